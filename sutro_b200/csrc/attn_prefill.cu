@@ -1,0 +1,256 @@
+// sutro_b200 — K3: causal prefill attention over the paged KV cache (varlen).
+//
+// The prompt's K/V have already been written to the cache by rope_kv_write, so
+// new tokens attend to [cached prefix | themselves] through one code path; a
+// shared system-prompt prefix is just a run of shared page ids.
+//
+// Work decomposition: CTA = (q tile, kv head) of one sequence.  The CTA has 8
+// warps = G query heads x (QT/16) token sub-tiles, QT = 128/G, so all heads of
+// a GQA group reuse each K/V page loaded into shared memory.  Pages stream
+// through a 4-stage cp.async.bulk ring (flat 8 KiB copies of pre-swizzled
+// tiles, see kernels.h); math is FlashAttention-2 style on mma.sync m16n8k16
+// with fp32 online softmax.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+namespace {
+
+constexpr int kPfWarps = 8;
+constexpr int kPfStages = 4;
+constexpr int kPfStageBytes = 2 * kTileBytes;
+constexpr int kPfSmem = kPfStages * kPfStageBytes + 1024;
+
+template <int G>
+__global__ void __launch_bounds__(kPfWarps * 32)
+attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                    const __nv_bfloat16* __restrict__ kv_layer,
+                    const int32_t* __restrict__ page_table, int max_pages,
+                    const int32_t* __restrict__ work, const int32_t* __restrict__ seq_slot,
+                    const int32_t* __restrict__ seq_q_start, const int32_t* __restrict__ seq_q_len,
+                    const int32_t* __restrict__ seq_past, int hq, int hkv, float scale_log2) {
+  constexpr int QT = 128 / G;  // query tokens per CTA
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+  __shared__ uint64_t full_bar[kPfStages];
+
+  const int seq = work[2 * blockIdx.x];
+  const int qt0 = work[2 * blockIdx.x + 1];
+  const int kvh = blockIdx.y;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int slot = seq_slot[seq];
+  const int q_start = seq_q_start[seq];
+  const int q_len = seq_q_len[seq];
+  const int past = seq_past[seq];
+  const int32_t* pt = page_table + static_cast<size_t>(slot) * max_pages;
+
+  const int head = kvh * G + (warp % G);      // query head of this warp
+  const int sub = warp / G;                   // 16-token sub-tile of this warp
+  const int q0 = qt0 + sub * 16;              // first query token (within the sequence's new tokens)
+  const int cta_q_end = min(qt0 + QT, q_len);  // exclusive
+  const int last_kv_pos = past + cta_q_end - 1;
+  const int n_tiles = last_kv_pos / kPageTokens + 1;
+  const int warp_last_pos = past + min(q0 + 16, q_len) - 1;  // causal horizon of this warp
+  const bool warp_active = q0 < q_len;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kPfStages; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int tile, int stage) {
+    const int page = pt[tile];
+    const __nv_bfloat16* src =
+        kv_layer + (static_cast<size_t>(page) * hkv + kvh) * (2 * kTileElems);
+    const uint32_t bar = smem_u32(&full_bar[stage]);
+    mbar_arrive_expect_tx(bar, kPfStageBytes);
+    bulk_load_1d(smem_u32(smem + stage * kPfStageBytes), src, kPfStageBytes, bar);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kPfStages - 1; ++s)
+      if (s < n_tiles) issue(s, s);
+  }
+
+  // Q fragments for this warp's 16 tokens x 128 dims.
+  const int ldq = (hq + 2 * hkv) * kHeadDim;
+  const int r0 = lane >> 2;
+  uint32_t qa[8][4];
+  {
+    const int t0 = q0 + r0, t1 = q0 + r0 + 8;
+    const __nv_bfloat16* p0 =
+        qkv + static_cast<size_t>(q_start + t0) * ldq + head * kHeadDim + 2 * (lane & 3);
+    const __nv_bfloat16* p1 = p0 + static_cast<size_t>(8) * ldq;
+    const bool v0 = t0 < q_len, v1 = t1 < q_len;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      qa[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(p0 + kk * 16) : 0u;
+      qa[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(p1 + kk * 16) : 0u;
+      qa[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(p0 + kk * 16 + 8) : 0u;
+      qa[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(p1 + kk * 16 + 8) : 0u;
+    }
+  }
+
+  float o[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  const int pos_r0 = past + q0 + r0;  // absolute position of row r0 (row r0+8: +8)
+
+  const int lm = lane >> 3;
+  const int lr = lane & 7;
+
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int stage = tile % kPfStages;
+    const uint32_t phase = (tile / kPfStages) & 1;
+    // keep the ring full: the stage freed by the previous iteration's barrier
+    if (threadIdx.x == 0) {
+      const int nxt = tile + kPfStages - 1;
+      if (nxt < n_tiles) {
+        fence_proxy_async_smem();
+        issue(nxt, nxt % kPfStages);
+      }
+    }
+    mbar_wait(smem_u32(&full_bar[stage]), phase);
+
+    if (warp_active && tile * kPageTokens <= warp_last_pos) {
+      const uint32_t ks = smem_u32(smem + stage * kPfStageBytes);
+      const uint32_t vs = ks + kTileBytes;
+      float s0[4] = {0.f, 0.f, 0.f, 0.f};
+      float s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const int tok = (lm >> 1) * 8 + lr;
+        const int chunk = kk * 2 + (lm & 1);
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(ks + tok * 256 + ((chunk ^ (tok & 7)) << 4), b0, b1, b2, b3);
+        mma_bf16_16816(s0, qa[kk], b0, b1);
+        mma_bf16_16816(s1, qa[kk], b2, b3);
+      }
+      // causal mask: kv position > query position
+      const int kp = tile * kPageTokens + 2 * (lane & 3);
+      float sv[2][4] = {{s0[0], s0[1], s1[0], s1[1]}, {s0[2], s0[3], s1[2], s1[3]}};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int qp = pos_r0 + 8 * h;
+        if (kp > qp) sv[h][0] = -INFINITY;
+        if (kp + 1 > qp) sv[h][1] = -INFINITY;
+        if (kp + 8 > qp) sv[h][2] = -INFINITY;
+        if (kp + 9 > qp) sv[h][3] = -INFINITY;
+      }
+      float alpha[2];
+      uint32_t pa[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float mx = fmaxf(fmaxf(sv[h][0], sv[h][1]), fmaxf(sv[h][2], sv[h][3]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float m_new = fmaxf(m_run[h], mx);
+        // a row can be fully masked in this tile only if an earlier tile already
+        // gave it a finite max (position 0 is always visible), except for padding rows
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        alpha[h] = exp2f((m_run[h] - m_use) * scale_log2);
+        float p[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = exp2f((sv[h][i] - m_use) * scale_log2);
+        float ps = p[0] + p[1] + p[2] + p[3];
+        ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+        ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+        l_run[h] = l_run[h] * alpha[h] + ps;
+        m_run[h] = m_new;
+        pa[h] = pack_bf16x2(p[0], p[1]);
+        pa[2 + h] = pack_bf16x2(p[2], p[3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 16; nt += 2) {
+        const int tok = (lm & 1) * 8 + lr;
+        const int chunk = nt + (lm >> 1);
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(vs + tok * 256 + ((chunk ^ (tok & 7)) << 4), b0, b1, b2, b3);
+        o[nt][0] *= alpha[0];
+        o[nt][1] *= alpha[0];
+        o[nt][2] *= alpha[1];
+        o[nt][3] *= alpha[1];
+        o[nt + 1][0] *= alpha[0];
+        o[nt + 1][1] *= alpha[0];
+        o[nt + 1][2] *= alpha[1];
+        o[nt + 1][3] *= alpha[1];
+        mma_bf16_16816(o[nt], pa, b0, b1);
+        mma_bf16_16816(o[nt + 1], pa, b2, b3);
+      }
+    }
+    __syncthreads();  // everyone is done with this stage -> it may be refilled
+  }
+
+  if (warp_active) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = q0 + r0 + 8 * h;
+      if (t >= q_len) continue;
+      const float inv = 1.0f / l_run[h];
+      __nv_bfloat16* op = out + static_cast<size_t>(q_start + t) * hq * kHeadDim +
+                          head * kHeadDim + 2 * (lane & 3);
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        *reinterpret_cast<__nv_bfloat162*>(op + nt * 8) =
+            __floats2bfloat162_rn(o[nt][2 * h] * inv, o[nt][2 * h + 1] * inv);
+      }
+    }
+  }
+}
+
+template <int G>
+int launch(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
+           int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
+           const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past, int hq,
+           int hkv, float scale, cudaStream_t stream) {
+  auto kern = attn_prefill_kernel<G>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmem));
+    attr_set = true;
+  }
+  dim3 grid(n_work, hkv);
+  kern<<<grid, kPfWarps * 32, kPfSmem, stream>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
+      static_cast<const __nv_bfloat16*>(kv_layer), page_table, max_pages, work, seq_slot,
+      seq_q_start, seq_q_len, seq_past, hq, hkv, scale * 1.4426950408889634f);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int attn_prefill_q_tile(int hq, int hkv) { return 128 / (hq / hkv); }
+
+int attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
+                 int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
+                 const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past,
+                 int hq, int hkv, float scale, cudaStream_t stream) {
+  if (n_work <= 0) return 0;
+  if (hkv <= 0 || hq % hkv != 0) {
+    set_last_error("attn_prefill: hq=%d not a multiple of hkv=%d", hq, hkv);
+    return -1;
+  }
+#define SB_PF(G)                                                                               \
+  return launch<G>(qkv, out, kv_layer, page_table, max_pages, work, n_work, seq_slot,         \
+                   seq_q_start, seq_q_len, seq_past, hq, hkv, scale, stream)
+  switch (hq / hkv) {
+    case 1: SB_PF(1);
+    case 2: SB_PF(2);
+    case 4: SB_PF(4);
+    case 8: SB_PF(8);
+    default:
+      set_last_error("attn_prefill: unsupported GQA group size %d", hq / hkv);
+      return -1;
+  }
+#undef SB_PF
+}
+
+}  // namespace sb

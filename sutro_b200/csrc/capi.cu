@@ -1,0 +1,96 @@
+// sutro_b200 — C-ABI (see include/sutro_b200.h).  Plain pointers and sizes,
+// integer status codes, never throws across the boundary.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/sutro_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+static thread_local char g_err[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+}  // namespace sb
+
+using namespace sb;
+
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+const char* sb200_last_error(void) { return last_error(); }
+int sb200_abi_version(void) { return SB200_ABI_VERSION; }
+
+int sb200_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+  int dev = 0;
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  SB_CUDA_CHECK(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (total_mem) *total_mem = p.totalGlobalMem;
+  return 0;
+}
+
+int sb200_gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* resid, int M,
+                       int N, int K, int ldd, int epilogue, int block_n, void* stream) {
+  return gemm_bf16_tn(a, a_rows, w, d, resid, M, N, K, ldd, epilogue, block_n, STREAM(stream));
+}
+
+int sb200_rmsnorm(const void* x, const void* w, void* out, int rows, int d, float eps,
+                  void* stream) {
+  return rmsnorm(x, w, out, rows, d, eps, STREAM(stream));
+}
+
+int sb200_embed_gather(const int32_t* ids, const void* table, void* out, int rows, int d,
+                       void* stream) {
+  return embed_gather(ids, table, out, rows, d, STREAM(stream));
+}
+
+int sb200_l2_normalize_rows(const void* x, float* out, int rows, int d, void* stream) {
+  return l2_normalize_rows(x, out, rows, d, STREAM(stream));
+}
+
+int sb200_rope_kv_write(void* qkv, const void* q_norm_w, const void* k_norm_w, const void* cos_tab,
+                        const void* sin_tab, const int32_t* tok_slot, const int32_t* tok_pos,
+                        const int32_t* page_table, int max_pages, void* kv_layer, int T, int hq,
+                        int hkv, float eps, void* stream) {
+  return rope_kv_write(qkv, q_norm_w, k_norm_w, cos_tab, sin_tab, tok_slot, tok_pos, page_table,
+                       max_pages, kv_layer, T, hq, hkv, eps, STREAM(stream));
+}
+
+int sb200_attn_decode(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
+                      int max_pages, const int32_t* row_slot, const int32_t* ctx_len, int B, int hq,
+                      int hkv, float scale, void* stream) {
+  return attn_decode(qkv, out, kv_layer, page_table, max_pages, row_slot, ctx_len, B, hq, hkv,
+                     scale, STREAM(stream));
+}
+
+int sb200_attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
+                       int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
+                       const int32_t* seq_q_start, const int32_t* seq_q_len,
+                       const int32_t* seq_past, int hq, int hkv, float scale, void* stream) {
+  return attn_prefill(qkv, out, kv_layer, page_table, max_pages, work, n_work, seq_slot,
+                      seq_q_start, seq_q_len, seq_past, hq, hkv, scale, STREAM(stream));
+}
+
+int sb200_attn_prefill_q_tile(int hq, int hkv) { return attn_prefill_q_tile(hq, hkv); }
+
+int sb200_fsm_build_mask(const int32_t* fsm_trans, const uint8_t* fsm_accept, int n_states,
+                         const uint8_t* tok_bytes, const int32_t* tok_off, int vocab, int eos_id,
+                         uint32_t* mask_bits, int mask_words, void* stream) {
+  return fsm_build_mask(fsm_trans, fsm_accept, n_states, tok_bytes, tok_off, vocab, eos_id,
+                        mask_bits, mask_words, STREAM(stream));
+}
+
+}  // extern "C"

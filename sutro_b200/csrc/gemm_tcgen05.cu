@@ -1,0 +1,415 @@
+// sutro_b200 — K1: bf16 GEMM  D[M,N] = A[M,K] · W[N,K]^T  on tcgen05 tensor cores.
+//
+// Every projection of the transformer (QKV, O, gate/up, down, lm_head) has this
+// shape: activations row-major [tokens, K], weights row-major [N, K] — both
+// K-major, which is the native operand layout of tcgen05.mma with 128-byte
+// swizzled shared-memory tiles.
+//
+// Kernel anatomy (persistent, warp-specialised, one CTA per SM):
+//   warp 0    TMA producer: cp.async.bulk.tensor 2-D loads of A (128x64) and
+//             W (BLOCK_N x 64) tiles into a kStages-deep shared-memory ring.
+//   warp 1    MMA issuer: one lane issues tcgen05.mma (M=128, N=BLOCK_N, K=16)
+//             four times per stage, accumulating in TMEM; tcgen05.commit frees
+//             the stage / publishes the accumulator through mbarriers.
+//   warp 2    TMEM allocator (2 accumulator stages so the epilogue of tile i
+//             overlaps the main loop of tile i+1).
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused
+//             epilogue -> 64-byte-per-thread global stores.
+//
+// Fused epilogues (rounding points mirror the bf16 oracle, oracle/model_ref.py):
+//   STORE_BF16     D = bf16(acc)
+//   RESIDUAL_BF16  D = bf16(bf16(acc) + R)           (O-proj / down-proj + residual)
+//   SWIGLU_BF16    D[:, j] = bf16(silu(bf16(acc[2j])) * bf16(acc[2j+1]))
+//                  (gate/up weights interleaved row-wise; output has N/2 columns)
+//   STORE_F32      D = acc                             (lm_head logits)
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kAccStages = 2;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = kAccStages * BLOCK_N;  // 512 / 256 / 128: powers of two
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +align slack
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
+                    const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
+                    const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tempty_bar = bars + 2 * Cfg::kStages + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 2 * kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + kBlockM - 1) / kBlockM;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_k = K / kBlockK;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m;
+        const int n_blk = tile / num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb_ = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+          tma_load_2d(sa, &tm_a, fb, kb * kBlockK, m_blk * kBlockM);
+          tma_load_2d(sb_, &tm_b, fb, kb * kBlockK, n_blk * BLOCK_N);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle span: +2 in 16-byte units
+            tc_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(smem_u32(&empty_bar[stage]));
+          if (kb == num_k - 1) tc_commit(smem_u32(&tfull_bar[acc]));
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % num_m;
+      const int n_blk = tile / num_m;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * kBlockM + q * 32 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + acc * BLOCK_N + c * 32 + (static_cast<uint32_t>(q * 32) << 16),
+                      v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (!row_ok || col0 >= N) continue;
+        if constexpr (EPI == EPI_STORE_F32) {
+          float* dp = reinterpret_cast<float*>(d_out) + static_cast<size_t>(row) * ldd + col0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st_v4(dp + 4 * i, make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        } else if constexpr (EPI == EPI_SWIGLU_BF16) {
+          __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(d_out) +
+                              static_cast<size_t>(row) * ldd + (col0 >> 1);
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float r2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float g = bf16_round(__uint_as_float(v[4 * i + 2 * h]));
+              const float u = bf16_round(__uint_as_float(v[4 * i + 2 * h + 1]));
+              const float s = bf16_round(g / (1.0f + __expf(-g)));
+              r2[h] = s * u;
+            }
+            o[i] = pack_bf16x2(r2[0], r2[1]);
+          }
+          st_v4(dp, make_uint4(o[0], o[1], o[2], o[3]));
+          st_v4(dp + 8, make_uint4(o[4], o[5], o[6], o[7]));
+        } else {
+          __nv_bfloat16* dp =
+              reinterpret_cast<__nv_bfloat16*>(d_out) + static_cast<size_t>(row) * ldd + col0;
+          uint32_t o[16];
+          if constexpr (EPI == EPI_RESIDUAL_BF16) {
+            const __nv_bfloat16* rp = resid + static_cast<size_t>(row) * ldd + col0;
+            uint4 rv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rv[i] = *reinterpret_cast<const uint4*>(rp + 8 * i);
+            const uint32_t* ru = reinterpret_cast<const uint32_t*>(rv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 r = unpack_bf16x2(ru[i]);
+              o[i] = pack_bf16x2(bf16_round(__uint_as_float(v[2 * i])) + r.x,
+                                 bf16_round(__uint_as_float(v[2 * i + 1])) + r.y);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              o[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            st_v4(dp + 8 * i, make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int rows, cols, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= (static_cast<size_t>(k.rows) * 0x9E3779B97F4A7C15ull) ^
+         (static_cast<size_t>(k.cols) << 20) ^ (static_cast<size_t>(k.box_rows) << 50);
+    return h;
+  }
+};
+
+// Row-major bf16 [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle.
+int make_tmap(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, rows, cols, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable");
+    return -1;
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: %d (ptr=%p rows=%d cols=%d box_rows=%d)",
+                   static_cast<int>(r), ptr, rows, cols, box_rows);
+    return -1;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  cache.emplace(key, *out);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N, int EPI>
+int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* resid, int M, int N,
+               int K, int ldd, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap tm_a, tm_b;
+  if (make_tmap(a, a_rows, K, kBlockM, &tm_a)) return -1;
+  if (make_tmap(w, N, K, BLOCK_N, &tm_b)) return -1;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(
+      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI>
+int launch_epi(int block_n, const void* a, int a_rows, const void* w, void* d, const void* resid,
+               int M, int N, int K, int ldd, cudaStream_t stream) {
+  switch (block_n) {
+    case 64:
+      return launch_cfg<64, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+    case 128:
+      return launch_cfg<128, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+    default:
+      return launch_cfg<256, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+  }
+}
+
+}  // namespace
+
+int gemm_pick_block_n(int M, int N) {
+  const int num_m = (M + kBlockM - 1) / kBlockM;
+  const int sms = num_sms();
+  // Largest tile that still gives every SM at least one tile; wide tiles
+  // amortise the A-operand shared-memory traffic, narrow ones fill the chip
+  // when the token batch is small.
+  for (int bn : {256, 128}) {
+    if (N % bn != 0 && N > bn) {
+      if (bn == 256 && N % 128 == 0) continue;  // prefer an exact tiling
+    }
+    if (num_m * ((N + bn - 1) / bn) >= sms) return bn;
+  }
+  return 64;
+}
+
+int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* resid, int M,
+                 int N, int K, int ldd, int epilogue, int block_n, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  if (K % kBlockK != 0 || N % 32 != 0 || a_rows < M) {
+    set_last_error("gemm_bf16_tn: unsupported shape M=%d N=%d K=%d a_rows=%d", M, N, K, a_rows);
+    return -1;
+  }
+  if (block_n == 0) block_n = gemm_pick_block_n(M, N);
+  if (block_n != 64 && block_n != 128 && block_n != 256) {
+    set_last_error("gemm_bf16_tn: block_n must be 64/128/256, got %d", block_n);
+    return -1;
+  }
+  switch (epilogue) {
+    case EPI_STORE_BF16:
+      return launch_epi<EPI_STORE_BF16>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream);
+    case EPI_RESIDUAL_BF16:
+      if (!resid) {
+        set_last_error("gemm_bf16_tn: residual epilogue without residual pointer");
+        return -1;
+      }
+      return launch_epi<EPI_RESIDUAL_BF16>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream);
+    case EPI_SWIGLU_BF16:
+      return launch_epi<EPI_SWIGLU_BF16>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream);
+    case EPI_STORE_F32:
+      return launch_epi<EPI_STORE_F32>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream);
+    default:
+      set_last_error("gemm_bf16_tn: unknown epilogue %d", epilogue);
+      return -1;
+  }
+}
+
+}  // namespace sb

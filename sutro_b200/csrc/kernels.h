@@ -1,0 +1,109 @@
+// sutro_b200 — internal launcher declarations shared by the kernels, the engine
+// and the C-ABI (capi.cu).  All launchers return 0 on success, -1 on error
+// (message retrievable through sb::last_error()).  No launcher synchronises.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+const char* last_error();
+void set_last_error(const char* fmt, ...);
+
+// ---------------------------------------------------------------------------
+// geometry of the paged KV cache (see DESIGN.md "data layout in HBM")
+//   pool[layer][page][kv_head][K|V][kPageTokens][kHeadDim]  bf16
+//   inside one [16][128] tile the 16-byte chunk c of token row r is stored at
+//   chunk position c ^ (r & 7): a flat 4 KiB bulk copy then lands in shared
+//   memory already bank-conflict-free for ldmatrix.
+// ---------------------------------------------------------------------------
+constexpr int kHeadDim = 128;
+constexpr int kPageTokens = 16;
+constexpr int kTileElems = kPageTokens * kHeadDim;   // one K (or V) tile of one head
+constexpr int kTileBytes = kTileElems * 2;           // 4096
+
+enum GemmEpilogue {
+  EPI_STORE_BF16 = 0,
+  EPI_RESIDUAL_BF16 = 1,
+  EPI_SWIGLU_BF16 = 2,
+  EPI_STORE_F32 = 3,
+};
+
+// K1 — D = A · W^T (+ fused epilogue); A:[a_rows>=M, K] bf16, W:[N,K] bf16.
+int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* resid, int M,
+                 int N, int K, int ldd, int epilogue, int block_n, cudaStream_t stream);
+int gemm_pick_block_n(int M, int N);
+
+// K4 — RMSNorm over rows: out = bf16(w * bf16(x * rsqrt(mean(x^2) + eps))).
+int rmsnorm(const void* x, const void* w, void* out, int rows, int d, float eps,
+            cudaStream_t stream);
+
+// K9a — embedding gather: out[t,:] = table[ids[t],:].
+int embed_gather(const int32_t* ids, const void* table, void* out, int rows, int d,
+                 cudaStream_t stream);
+// gather rows of x by index (last-token selection before the lm_head).
+int gather_rows(const int32_t* idx, const void* x, void* out, int rows, int d,
+                cudaStream_t stream);
+
+// K5 — per-head q/k RMSNorm (optional) + RoPE on q and k, K/V scatter into the
+// paged cache.  qkv:[T, (hq+2*hkv)*128] is updated in place for q.
+int rope_kv_write(void* qkv, const void* q_norm_w, const void* k_norm_w, const void* cos_tab,
+                  const void* sin_tab, const int32_t* tok_slot, const int32_t* tok_pos,
+                  const int32_t* page_table, int max_pages, void* kv_layer, int T, int hq,
+                  int hkv, float eps, cudaStream_t stream);
+
+// K2 — paged-KV decode attention (one query token per sequence).
+int attn_decode(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
+                int max_pages, const int32_t* row_slot, const int32_t* ctx_len, int B, int hq,
+                int hkv, float scale, cudaStream_t stream);
+
+// K3 — causal prefill attention over the paged cache (varlen batch).
+// work: [n_work] {seq, q_tile_start}; per-seq arrays are indexed by seq.
+int attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
+                 int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
+                 const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past,
+                 int hq, int hkv, float scale, cudaStream_t stream);
+int attn_prefill_q_tile(int hq, int hkv);
+
+// K8 — FSM token-mask build, masked greedy sampling + FSM advance.
+struct SampleArgs {
+  const float* logits;      // [B, ldl]
+  int ldl;
+  int vocab;
+  int B;
+  const int32_t* row_slot;  // [B] slot of each logits row
+  // per-slot decode state
+  int32_t* slot_state;      // FSM state (or -1 when unconstrained)
+  int32_t* slot_ngen;       // tokens generated so far
+  int32_t* slot_next_tok;   // out: sampled token (input of next step)
+  int32_t* slot_pos;        // position of next token (incremented)
+  int32_t* slot_done;       // out: 1 when the row finished at this step
+  const int32_t* slot_row;  // global row id of the slot
+  const int32_t* slot_maxnew;
+  int32_t* out_tokens;      // [n_rows, out_stride]
+  int32_t* out_len;         // [n_rows]
+  int out_stride;
+  // FSM tables (null when no schema)
+  const uint32_t* mask_bits;   // [n_states, mask_words]
+  int mask_words;
+  const int32_t* fsm_trans;    // [n_states, 256] byte transitions, -1 = dead
+  const uint8_t* fsm_accept;   // [n_states]
+  const uint8_t* fsm_final;    // [n_states] accepting with no outgoing edge
+  const uint8_t* tok_bytes;    // vocab byte blob
+  const int32_t* tok_off;      // [vocab+1]
+  int eos_id;
+  int ignore_eos;
+};
+int sample_greedy(const SampleArgs& a, cudaStream_t stream);
+int prepare_decode(const int32_t* row_slot, const int32_t* slot_next_tok, const int32_t* slot_pos,
+                   int32_t* tok_ids, int32_t* tok_pos, int32_t* tok_slot, int32_t* ctx_len, int B,
+                   cudaStream_t stream);
+int fsm_build_mask(const int32_t* fsm_trans, const uint8_t* fsm_accept, int n_states,
+                   const uint8_t* tok_bytes, const int32_t* tok_off, int vocab, int eos_id,
+                   uint32_t* mask_bits, int mask_words, cudaStream_t stream);
+
+// K9b — embedding head: last-token rows -> fp32 L2-normalised vectors.
+int l2_normalize_rows(const void* x, float* out, int rows, int d, cudaStream_t stream);
+
+}  // namespace sb

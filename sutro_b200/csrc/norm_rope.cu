@@ -1,0 +1,220 @@
+// sutro_b200 — K4/K5/K9: HBM-bound row kernels.
+//   rmsnorm            one warp per row, 16-byte vector loads, warp-shuffle reduce
+//   embed_gather       one warp per row copy
+//   rope_kv_write      per-head q/k RMSNorm (Qwen3) + rotate-half RoPE, K/V scatter
+//                      into the swizzled paged cache
+//   l2_normalize_rows  embedding head (fp32 out)
+// Rounding points follow the bf16 reference model (oracle/model_ref.py), which
+// restates transformers 5.5.0 modeling_qwen3.py:50-66 (RMSNorm), :151-180 (RoPE),
+// :248-264 (q/k norm before RoPE).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+namespace {
+
+constexpr int kRowWarps = 4;
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+               __nv_bfloat16* __restrict__ out, int rows, int d, float eps) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  uint4* orow = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * d);
+  const int nvec = d >> 3;
+  float ss = 0.f;
+  for (int i = lane; i < nvec; i += 32) {
+    const uint4 v = xr[i];
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(u[j]);
+      ss += f.x * f.x + f.y * f.y;
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
+  for (int i = lane; i < nvec; i += 32) {
+    const uint4 v = xr[i];  // second touch hits L1/L2
+    const uint4 g = wr[i];
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(u[j]);
+      const float2 wv = unpack_bf16x2(gw[j]);
+      o[j] = pack_bf16x2(wv.x * bf16_round(f.x * rstd), wv.y * bf16_round(f.y * rstd));
+    }
+    orow[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+gather_rows_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                   __nv_bfloat16* __restrict__ out, int rows, int d) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* src = reinterpret_cast<const uint4*>(table + static_cast<size_t>(ids[row]) * d);
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * d);
+  for (int i = lane; i < (d >> 3); i += 32) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+l2norm_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int rows, int d) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const __nv_bfloat162* xr =
+      reinterpret_cast<const __nv_bfloat162*>(x + static_cast<size_t>(row) * d);
+  float ss = 0.f;
+  for (int i = lane; i < (d >> 1); i += 32) {
+    const float2 f = __bfloat1622float2(xr[i]);
+    ss += f.x * f.x + f.y * f.y;
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  float2* orow = reinterpret_cast<float2*>(out + static_cast<size_t>(row) * d);
+  for (int i = lane; i < (d >> 1); i += 32) {
+    const float2 f = __bfloat1622float2(xr[i]);
+    orow[i] = make_float2(f.x * inv, f.y * inv);
+  }
+}
+
+// One CTA per token, one warp per head (looping).  Lane l owns dims {2l, 2l+1}
+// and {64+2l, 64+2l+1}: the rotate-half partner of a dim lives in the same lane.
+constexpr int kRopeWarps = 8;
+
+__global__ void __launch_bounds__(kRopeWarps * 32)
+rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ q_norm_w,
+               const __nv_bfloat16* __restrict__ k_norm_w, const __nv_bfloat16* __restrict__ cos_t,
+               const __nv_bfloat16* __restrict__ sin_t, const int32_t* __restrict__ tok_slot,
+               const int32_t* __restrict__ tok_pos, const int32_t* __restrict__ page_table,
+               int max_pages, __nv_bfloat16* __restrict__ kv_layer, int hq, int hkv, float eps) {
+  const int t = blockIdx.x;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pos = tok_pos[t];
+  const int slot = tok_slot[t];
+  const int page = page_table[static_cast<size_t>(slot) * max_pages + pos / kPageTokens];
+  const int r = pos % kPageTokens;
+  const int nheads = hq + 2 * hkv;
+  __nv_bfloat16* row = qkv + static_cast<size_t>(t) * nheads * kHeadDim;
+
+  // cos/sin tables: [max_pos, 64] bf16 (already rounded like the reference does).
+  const float2 cs_c = __bfloat1622float2(
+      *reinterpret_cast<const __nv_bfloat162*>(cos_t + static_cast<size_t>(pos) * 64 + 2 * lane));
+  const float2 cs_s = __bfloat1622float2(
+      *reinterpret_cast<const __nv_bfloat162*>(sin_t + static_cast<size_t>(pos) * 64 + 2 * lane));
+
+  for (int h = warp; h < nheads; h += kRopeWarps) {
+    __nv_bfloat16* hp = row + h * kHeadDim;
+    float2 lo = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(hp + 2 * lane));
+    float2 hi = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(hp + 64 + 2 * lane));
+    const bool is_q = h < hq;
+    const bool is_k = !is_q && h < hq + hkv;
+    if (is_q || is_k) {
+      const __nv_bfloat16* nw = is_q ? q_norm_w : k_norm_w;
+      if (nw != nullptr) {
+        float ss = lo.x * lo.x + lo.y * lo.y + hi.x * hi.x + hi.y * hi.y;
+        ss = warp_sum(ss);
+        const float rstd = rsqrtf(ss / static_cast<float>(kHeadDim) + eps);
+        const float2 wl =
+            __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(nw + 2 * lane));
+        const float2 wh =
+            __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(nw + 64 + 2 * lane));
+        lo.x = bf16_round(wl.x * bf16_round(lo.x * rstd));
+        lo.y = bf16_round(wl.y * bf16_round(lo.y * rstd));
+        hi.x = bf16_round(wh.x * bf16_round(hi.x * rstd));
+        hi.y = bf16_round(wh.y * bf16_round(hi.y * rstd));
+      }
+      // out[i]    = x[i]*cos - x[i+64]*sin ; out[i+64] = x[i+64]*cos + x[i]*sin
+      float2 olo, ohi;
+      olo.x = bf16_round(lo.x * cs_c.x) + bf16_round(-hi.x * cs_s.x);
+      olo.y = bf16_round(lo.y * cs_c.y) + bf16_round(-hi.y * cs_s.y);
+      ohi.x = bf16_round(hi.x * cs_c.x) + bf16_round(lo.x * cs_s.x);
+      ohi.y = bf16_round(hi.y * cs_c.y) + bf16_round(lo.y * cs_s.y);
+      lo = olo;
+      hi = ohi;
+    }
+    const __nv_bfloat162 plo = __floats2bfloat162_rn(lo.x, lo.y);
+    const __nv_bfloat162 phi = __floats2bfloat162_rn(hi.x, hi.y);
+    if (is_q) {
+      *reinterpret_cast<__nv_bfloat162*>(hp + 2 * lane) = plo;
+      *reinterpret_cast<__nv_bfloat162*>(hp + 64 + 2 * lane) = phi;
+    } else {
+      const int kvh = is_k ? (h - hq) : (h - hq - hkv);
+      __nv_bfloat16* tile = kv_layer +
+                            (static_cast<size_t>(page) * hkv + kvh) * (2 * kTileElems) +
+                            (is_k ? 0 : kTileElems) + r * kHeadDim;
+      const int c_lo = lane >> 2;  // 16-byte chunk of dims 2l..2l+1
+      const int c_hi = c_lo + 8;
+      const int within = (2 * lane) & 7;
+      *reinterpret_cast<__nv_bfloat162*>(tile + ((c_lo ^ (r & 7)) << 3) + within) = plo;
+      *reinterpret_cast<__nv_bfloat162*>(tile + ((c_hi ^ (r & 7)) << 3) + within) = phi;
+    }
+  }
+}
+
+}  // namespace
+
+int rmsnorm(const void* x, const void* w, void* out, int rows, int d, float eps,
+            cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (d % 8 != 0) {
+    set_last_error("rmsnorm: d=%d must be a multiple of 8", d);
+    return -1;
+  }
+  rmsnorm_kernel<<<(rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
+      static_cast<__nv_bfloat16*>(out), rows, d, eps);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int embed_gather(const int32_t* ids, const void* table, void* out, int rows, int d,
+                 cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (d % 8 != 0) {
+    set_last_error("embed_gather: d=%d must be a multiple of 8", d);
+    return -1;
+  }
+  gather_rows_kernel<<<(rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, stream>>>(
+      ids, static_cast<const __nv_bfloat16*>(table), static_cast<__nv_bfloat16*>(out), rows, d);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int gather_rows(const int32_t* idx, const void* x, void* out, int rows, int d,
+                cudaStream_t stream) {
+  return embed_gather(idx, x, out, rows, d, stream);
+}
+
+int l2_normalize_rows(const void* x, float* out, int rows, int d, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  l2norm_kernel<<<(rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), out, rows, d);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int rope_kv_write(void* qkv, const void* q_norm_w, const void* k_norm_w, const void* cos_tab,
+                  const void* sin_tab, const int32_t* tok_slot, const int32_t* tok_pos,
+                  const int32_t* page_table, int max_pages, void* kv_layer, int T, int hq,
+                  int hkv, float eps, cudaStream_t stream) {
+  if (T <= 0) return 0;
+  rope_kv_kernel<<<T, kRopeWarps * 32, 0, stream>>>(
+      static_cast<__nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(q_norm_w),
+      static_cast<const __nv_bfloat16*>(k_norm_w), static_cast<const __nv_bfloat16*>(cos_tab),
+      static_cast<const __nv_bfloat16*>(sin_tab), tok_slot, tok_pos, page_table, max_pages,
+      static_cast<__nv_bfloat16*>(kv_layer), hq, hkv, eps);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sb
