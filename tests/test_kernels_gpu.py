@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from sutro_b200 import _lib as L
-from tests import kv_layout as KV
+import kv_layout as KV
 
 pytestmark = pytest.mark.gpu
 
