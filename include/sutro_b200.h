@@ -80,6 +80,23 @@ int sb200_fsm_build_mask(const int32_t* fsm_trans, const uint8_t* fsm_accept, in
                          const uint8_t* tok_bytes, const int32_t* tok_off, int vocab, int eos_id,
                          uint32_t* mask_bits, int mask_words, void* stream);
 
+/* K7: batched byte-level BPE on the GPU.  merges:[n,2] left/right ids in rank order
+ * (merged_ids NULL => id 256+rank); cls_table: 0x110000 bytes, Unicode class per code
+ * point (0 other, 1 letter, 2 number, 3 white space); digits: max digits per pre-token
+ * (1 Qwen, 3 Llama-3); tok_bytes/tok_off: vocabulary byte strings (host pointers).
+ * encode/decode take DEVICE pointers; out_tokens_dev needs capacity n_bytes;
+ * decode with out_bytes_dev == NULL only fills row_byte_off_dev (sizing pass). */
+int sb200_tokenizer_create(const int32_t* merges, int n_merges, const int32_t* merged_ids,
+                           const uint8_t* cls_table, int digits, const uint8_t* tok_bytes,
+                           const int32_t* tok_off, int vocab, void** out);
+void sb200_tokenizer_destroy(void* tok);
+int sb200_tokenizer_encode(void* tok, const uint8_t* text_dev, int64_t n_bytes,
+                           const int64_t* row_off_dev, int64_t n_rows, int32_t* out_tokens_dev,
+                           int64_t* row_tok_off_dev, void* stream);
+int sb200_tokenizer_decode(void* tok, const int32_t* toks_dev, int64_t n_tok,
+                           const int64_t* row_tok_off_dev, int64_t n_rows, uint8_t* out_bytes_dev,
+                           int64_t* row_byte_off_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

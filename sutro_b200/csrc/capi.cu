@@ -93,4 +93,27 @@ int sb200_fsm_build_mask(const int32_t* fsm_trans, const uint8_t* fsm_accept, in
                         mask_bits, mask_words, STREAM(stream));
 }
 
+int sb200_tokenizer_create(const int32_t* merges, int n_merges, const int32_t* merged_ids,
+                           const uint8_t* cls_table, int digits, const uint8_t* tok_bytes,
+                           const int32_t* tok_off, int vocab, void** out) {
+  Tokenizer* t = nullptr;
+  const int rc = tokenizer_create(merges, n_merges, merged_ids, cls_table, digits, tok_bytes,
+                                  tok_off, vocab, &t);
+  *out = t;
+  return rc;
+}
+void sb200_tokenizer_destroy(void* tok) { tokenizer_destroy(static_cast<Tokenizer*>(tok)); }
+int sb200_tokenizer_encode(void* tok, const uint8_t* text_dev, int64_t n_bytes,
+                           const int64_t* row_off_dev, int64_t n_rows, int32_t* out_tokens_dev,
+                           int64_t* row_tok_off_dev, void* stream) {
+  return tokenizer_encode(static_cast<Tokenizer*>(tok), text_dev, n_bytes, row_off_dev, n_rows,
+                          out_tokens_dev, row_tok_off_dev, STREAM(stream));
+}
+int sb200_tokenizer_decode(void* tok, const int32_t* toks_dev, int64_t n_tok,
+                           const int64_t* row_tok_off_dev, int64_t n_rows, uint8_t* out_bytes_dev,
+                           int64_t* row_byte_off_dev, void* stream) {
+  return tokenizer_decode(static_cast<Tokenizer*>(tok), toks_dev, n_tok, row_tok_off_dev, n_rows,
+                          out_bytes_dev, row_byte_off_dev, STREAM(stream));
+}
+
 }  // extern "C"

@@ -103,6 +103,21 @@ int fsm_build_mask(const int32_t* fsm_trans, const uint8_t* fsm_accept, int n_st
                    const uint8_t* tok_bytes, const int32_t* tok_off, int vocab, int eos_id,
                    uint32_t* mask_bits, int mask_words, cudaStream_t stream);
 
+// K7 — GPU byte-level BPE tokenizer / detokenizer (tokenizer.cu).
+struct Tokenizer;
+int tokenizer_create(const int32_t* merges, int n_merges, const int32_t* merged_ids,
+                     const uint8_t* cls_table, int digits, const uint8_t* tok_bytes,
+                     const int32_t* tok_off, int vocab, Tokenizer** out);
+void tokenizer_destroy(Tokenizer* t);
+const uint8_t* tokenizer_tok_bytes(const Tokenizer* t);
+const int32_t* tokenizer_tok_off(const Tokenizer* t);
+int tokenizer_encode(Tokenizer* t, const uint8_t* text_dev, int64_t n_bytes,
+                     const int64_t* row_off_dev, int64_t n_rows, int32_t* out_tokens_dev,
+                     int64_t* row_tok_off_dev, cudaStream_t stream);
+int tokenizer_decode(Tokenizer* t, const int32_t* toks_dev, int64_t n_tok,
+                     const int64_t* row_tok_off_dev, int64_t n_rows, uint8_t* out_bytes_dev,
+                     int64_t* row_byte_off_dev, cudaStream_t stream);
+
 // K9b — embedding head: last-token rows -> fp32 L2-normalised vectors.
 int l2_normalize_rows(const void* x, float* out, int rows, int d, cudaStream_t stream);
 

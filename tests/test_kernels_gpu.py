@@ -200,9 +200,11 @@ def test_rope_kv_write(qk_norm):
     pt = torch.randperm(num_pages)[: n_slots * max_pages].view(n_slots, max_pages).to(torch.int32)
     pool = torch.zeros(num_pages, hkv, 2, KV.PAGE, KV.HD, dtype=torch.bfloat16, device=DEV)
     orig = qkv.clone()
+    # keep device copies alive across the launch (temporaries would be recycled)
+    d_slot, d_pos, d_pt = tok_slot.to(DEV), tok_pos.to(DEV), pt.to(DEV)
     L.check(L.lib().sb200_rope_kv_write(
-        L.ptr(qkv), L.ptr(qn), L.ptr(kn), L.ptr(cos), L.ptr(sin), L.ptr(tok_slot.to(DEV)),
-        L.ptr(tok_pos.to(DEV)), L.ptr(pt.to(DEV)), max_pages, L.ptr(pool), T, hq, hkv, 1e-6,
+        L.ptr(qkv), L.ptr(qn), L.ptr(kn), L.ptr(cos), L.ptr(sin), L.ptr(d_slot),
+        L.ptr(d_pos), L.ptr(d_pt), max_pages, L.ptr(pool), T, hq, hkv, 1e-6,
         stream()))
     torch.cuda.synchronize()
     x = orig.view(T, hq + 2 * hkv, KV.HD)
@@ -284,10 +286,11 @@ def test_attn_prefill(hq, hkv):
             work += [i, t0]
     i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
     scale = 1.0 / math.sqrt(KV.HD)
+    d_work, d_slot, d_qs = i32(work), i32(list(range(n))), i32(q_start)
+    d_ql, d_past = i32([q for _, q in specs]), i32([p for p, _ in specs])
     L.check(L.lib().sb200_attn_prefill(
-        L.ptr(qkv), L.ptr(out), L.ptr(pool), L.ptr(pt), max_pages, L.ptr(i32(work)),
-        len(work) // 2, L.ptr(i32(list(range(n)))), L.ptr(i32(q_start)),
-        L.ptr(i32([q for _, q in specs])), L.ptr(i32([p for p, _ in specs])), hq, hkv, scale,
+        L.ptr(qkv), L.ptr(out), L.ptr(pool), L.ptr(pt), max_pages, L.ptr(d_work),
+        len(work) // 2, L.ptr(d_slot), L.ptr(d_qs), L.ptr(d_ql), L.ptr(d_past), hq, hkv, scale,
         stream()))
     torch.cuda.synchronize()
     for i, (p, q) in enumerate(specs):
@@ -313,8 +316,9 @@ def test_fsm_build_mask_matches_python_walk():
     eos = 7
     words = (vocab + 31) // 32
     mask = torch.zeros(n_states, words, dtype=torch.int32, device=DEV)
-    L.check(L.lib().sb200_fsm_build_mask(L.ptr(trans.to(DEV)), L.ptr(accept.to(DEV)), n_states,
-                                         L.ptr(blob.to(DEV)), L.ptr(off.to(DEV)), vocab, eos,
+    d_trans, d_acc, d_blob, d_off = trans.to(DEV), accept.to(DEV), blob.to(DEV), off.to(DEV)
+    L.check(L.lib().sb200_fsm_build_mask(L.ptr(d_trans), L.ptr(d_acc), n_states,
+                                         L.ptr(d_blob), L.ptr(d_off), vocab, eos,
                                          L.ptr(mask), words, stream()))
     torch.cuda.synchronize()
     mask = mask.cpu()
