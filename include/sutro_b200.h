@@ -97,6 +97,89 @@ int sb200_tokenizer_decode(void* tok, const int32_t* toks_dev, int64_t n_tok,
                            const int64_t* row_tok_off_dev, int64_t n_rows, uint8_t* out_bytes_dev,
                            int64_t* row_byte_off_dev, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Engine-level entry points: the local replacement for the hosted service
+ * behind `POST batch-inference` / `POST job-results` (sutro/sdk.py:223, :384).
+ * One engine per GPU, driven from one host thread.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  /* architecture */
+  int n_layers, d_model, n_q_heads, n_kv_heads, d_ff, vocab, max_position;
+  float rms_eps;
+  int qk_norm;          /* Qwen3 per-head q/k RMSNorm                                  */
+  int embedding_model;  /* prefill-only: last-token pool + L2 normalise                */
+  int eos_id;
+  /* capacity */
+  int max_slots;          /* rows decoded concurrently                                 */
+  int max_prefill_tokens; /* new tokens per prefill forward                            */
+  int logit_chunk_rows;   /* lm_head / sampling rows per pass (bounds the fp32 logits) */
+  int min_admit_rows;     /* free slots to accumulate before interleaving a prefill    */
+  int64_t num_pages;      /* KV pool size in 16-token pages (all layers, all kv heads) */
+} sb200_engine_config;
+
+typedef struct {          /* device pointers, bf16, layouts as in sutro_b200/modelspec.py */
+  const void* embed;      /* [vocab, d_model]                                          */
+  const void* lm_head;    /* [vocab, d_model] (== embed when tied)                     */
+  const void* final_norm; /* [d_model]                                                 */
+  const void* rope_cos;   /* [max_position, 64]                                        */
+  const void* rope_sin;
+  const void* const* ln1; /* per layer [d_model]                                       */
+  const void* const* ln2;
+  const void* const* wqkv; /* per layer [(hq+2hkv)*128, d_model], rows q|k|v            */
+  const void* const* wo;   /* per layer [d_model, hq*128]                               */
+  const void* const* wgu;  /* per layer [2*d_ff, d_model], rows interleaved gate,up     */
+  const void* const* wd;   /* per layer [d_model, d_ff]                                 */
+  const void* const* q_norm; /* per layer [128] (qk_norm only)                          */
+  const void* const* k_norm;
+} sb200_engine_weights;
+
+/* progress record — same fields the reference streams from `stream-job-progress`
+ * (sutro/sdk.py:331-358): rows done, input tokens, output tokens. */
+typedef void (*sb200_progress_fn)(int64_t rows_done, int64_t input_tokens, int64_t output_tokens,
+                                  void* user);
+
+typedef struct {
+  /* inputs: one prompt per row = prefix_tokens | row tokens | suffix_tokens
+   * (stands in for payload["inputs"] + payload["system_prompt"], sutro/sdk.py:196-208) */
+  const int32_t* row_tokens_dev;  /* device: all rows' token ids, concatenated          */
+  const int64_t* row_tok_off_dev; /* device: [n_rows+1]                                 */
+  const int64_t* row_tok_off;     /* host copy of the same offsets                      */
+  int64_t n_rows;
+  const int32_t* prefix_tokens;   /* host */
+  int n_prefix;
+  const int32_t* suffix_tokens;   /* host */
+  int n_suffix;
+  int share_prefix;               /* reuse the prefix KV across rows (page granular)    */
+  int max_new_tokens;
+  int ignore_eos;
+  int truncate_rows;              /* payload["truncate_rows"], sutro/sdk.py:205          */
+  /* output_schema automaton (payload["json_schema"]), host arrays; fsm_states 0 = none */
+  const int32_t* fsm_trans;       /* [fsm_states, 256], -1 = dead                       */
+  const uint8_t* fsm_accept;
+  const uint8_t* fsm_final;
+  int fsm_states;
+  int fsm_start;
+  /* outputs, device, caller-allocated (results["outputs"], sutro/sdk.py:406)           */
+  int32_t* out_tokens_dev;        /* [n_rows, max_new_tokens]                           */
+  int32_t* out_len_dev;           /* [n_rows]                                           */
+  float* out_embed_dev;           /* [n_rows, d_model] (embedding models)               */
+  sb200_progress_fn progress;     /* may be NULL                                        */
+  void* progress_user;
+} sb200_job;
+
+typedef struct {
+  int64_t rows_done, input_tokens, prefill_tokens, decode_tokens;
+  int64_t prefill_steps, decode_steps, rows_truncated, prefix_cached_tokens;
+} sb200_job_stats;
+
+int sb200_engine_create(const sb200_engine_config* cfg, const sb200_engine_weights* w, void** out);
+void sb200_engine_destroy(void* engine);
+/* vocabulary byte strings (host): needed for output_schema masks and state advance */
+int sb200_engine_set_vocab(void* engine, const uint8_t* tok_bytes, const int32_t* tok_off);
+/* blocking; returns when every row has finished (non-zero: see sb200_last_error) */
+int sb200_engine_run(void* engine, const sb200_job* job, sb200_job_stats* stats);
+void* sb200_engine_stream(void* engine);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,716 @@
+// sutro_b200 — the batch-inference engine: what the reference leaves to its
+// hosted service after `POST batch-inference` (sutro/sdk.py:223): for N rows,
+// prefill + greedy decode over one model replica, with continuous batching, a
+// paged KV cache, shared-prefix reuse and constrained decoding.
+//
+// One engine == one GPU == one host thread.  All scheduling is host C++; every
+// arithmetic step is one of the kernels in this directory.  There is no CPU
+// compute path: if a launch fails the job fails.
+//
+// Memory plan: weights are caller-owned device tensors; the
+// engine owns the KV pool (num_pages x layers x hkv x 8 KiB), activation
+// workspaces sized for max(max_prefill_tokens, max_slots) tokens, a logits
+// chunk, the page table and the per-slot decode state.
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sutro_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+// ---- small device helpers owned by the engine -----------------------------
+struct SeqInit {  // one admitted row
+  int32_t slot, row, q_start, q_len, past, n_row_tok, max_new, fsm_start;
+};
+
+// Fill the flattened token batch of a prefill step from (prefix | row | suffix).
+__global__ void __launch_bounds__(128)
+prefill_prepare_kernel(const SeqInit* __restrict__ seqs, const int32_t* __restrict__ prefix,
+                       int n_prefix, const int32_t* __restrict__ suffix, int n_suffix,
+                       const int32_t* __restrict__ row_tokens,
+                       const int64_t* __restrict__ row_tok_off, int32_t* __restrict__ tok_ids,
+                       int32_t* __restrict__ tok_pos, int32_t* __restrict__ tok_slot,
+                       int32_t* __restrict__ last_idx) {
+  const SeqInit s = seqs[blockIdx.x];
+  const int64_t roff = s.row >= 0 ? row_tok_off[s.row] : 0;
+  for (int j = threadIdx.x; j < s.q_len; j += blockDim.x) {
+    const int p = s.past + j;
+    int tok;
+    if (p < n_prefix) {
+      tok = prefix[p];
+    } else if (p < n_prefix + s.n_row_tok) {
+      tok = row_tokens[roff + (p - n_prefix)];
+    } else {
+      tok = suffix[p - n_prefix - s.n_row_tok];
+    }
+    tok_ids[s.q_start + j] = tok;
+    tok_pos[s.q_start + j] = p;
+    tok_slot[s.q_start + j] = s.slot;
+  }
+  if (threadIdx.x == 0) last_idx[blockIdx.x] = s.q_start + s.q_len - 1;
+}
+
+// Install page-table rows and decode state for newly admitted rows.
+__global__ void __launch_bounds__(128)
+init_slots_kernel(const SeqInit* __restrict__ seqs, const int32_t* __restrict__ pt_rows,
+                  int max_pages, int32_t* __restrict__ page_table, int32_t* slot_state,
+                  int32_t* slot_ngen, int32_t* slot_pos, int32_t* slot_done, int32_t* slot_row,
+                  int32_t* slot_maxnew, int32_t* slot_next_tok) {
+  const SeqInit s = seqs[blockIdx.x];
+  for (int i = threadIdx.x; i < max_pages; i += blockDim.x)
+    page_table[static_cast<size_t>(s.slot) * max_pages + i] =
+        pt_rows[static_cast<size_t>(blockIdx.x) * max_pages + i];
+  if (threadIdx.x == 0) {
+    slot_state[s.slot] = s.fsm_start;
+    slot_ngen[s.slot] = 0;
+    slot_pos[s.slot] = s.past + s.q_len - 1;  // sampler increments: next position = prompt length
+    slot_done[s.slot] = 0;
+    slot_row[s.slot] = s.row;
+    slot_maxnew[s.slot] = s.max_new;
+    slot_next_tok[s.slot] = 0;
+  }
+}
+
+__global__ void scatter_embed_kernel(const float* __restrict__ src, const SeqInit* __restrict__ seqs,
+                                     float* __restrict__ dst, int d) {
+  const int row = seqs[blockIdx.x].row;
+  for (int i = threadIdx.x; i < d; i += blockDim.x)
+    dst[static_cast<size_t>(row) * d + i] = src[static_cast<size_t>(blockIdx.x) * d + i];
+}
+
+template <typename T>
+int dmalloc(T** p, size_t n) {
+  SB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return 0;
+}
+
+}  // namespace
+
+struct Engine {
+  sb200_engine_config cfg{};
+  sb200_engine_weights w{};
+  std::vector<const void*> ln1, ln2, wqkv, wo, wgu, wd, qn, kn;
+  cudaStream_t stream = nullptr;
+  int qkv_dim = 0, q_dim = 0, max_pages = 0, t_max = 0, logit_rows = 0, q_tile = 0;
+  int64_t num_pages = 0;
+  size_t layer_stride = 0;  // elements between consecutive layers in the KV pool
+
+  bf16 *x = nullptr, *h = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *hl = nullptr,
+       *hn = nullptr, *kv_pool = nullptr;
+  float *logits = nullptr, *embed_tmp = nullptr;
+  int32_t *tok_ids = nullptr, *tok_pos = nullptr, *tok_slot = nullptr, *ctx_len = nullptr,
+          *row_slot = nullptr, *last_idx = nullptr, *page_table = nullptr;
+  int32_t *slot_state = nullptr, *slot_ngen = nullptr, *slot_next_tok = nullptr,
+          *slot_pos = nullptr, *slot_done = nullptr, *slot_row = nullptr, *slot_maxnew = nullptr;
+  // staging
+  int32_t *h_stage = nullptr, *d_stage = nullptr;
+  size_t stage_cap = 0;  // int32 elements
+  int32_t* h_done = nullptr;
+  // vocabulary bytes + FSM tables
+  uint8_t* d_tok_bytes = nullptr;
+  int32_t* d_tok_off = nullptr;
+  int32_t* d_fsm_trans = nullptr;
+  uint8_t *d_fsm_accept = nullptr, *d_fsm_final = nullptr;
+  uint32_t* d_mask_bits = nullptr;
+  int mask_words = 0;
+  size_t fsm_cap_states = 0;
+  // job-scoped prompt pieces
+  int32_t *d_prefix = nullptr, *d_suffix = nullptr;
+  int prefix_cap = 0, suffix_cap = 0;
+  // host page allocator
+  std::vector<int32_t> free_pages;
+
+  ~Engine() {
+    for (void* p : {(void*)x, (void*)h, (void*)qkv, (void*)attn, (void*)act, (void*)hl, (void*)hn,
+                    (void*)kv_pool, (void*)logits, (void*)embed_tmp, (void*)tok_ids,
+                    (void*)tok_pos, (void*)tok_slot, (void*)ctx_len, (void*)row_slot,
+                    (void*)last_idx, (void*)page_table, (void*)slot_state, (void*)slot_ngen,
+                    (void*)slot_next_tok, (void*)slot_pos, (void*)slot_done, (void*)slot_row,
+                    (void*)slot_maxnew, (void*)d_stage, (void*)d_tok_bytes, (void*)d_tok_off,
+                    (void*)d_fsm_trans, (void*)d_fsm_accept, (void*)d_fsm_final,
+                    (void*)d_mask_bits, (void*)d_prefix, (void*)d_suffix})
+      cudaFree(p);
+    if (h_stage) cudaFreeHost(h_stage);
+    if (h_done) cudaFreeHost(h_done);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  bf16* kv_layer(int l) const { return kv_pool + static_cast<size_t>(l) * layer_stride; }
+
+  int init() {
+    const auto& c = cfg;
+    q_dim = c.n_q_heads * kHeadDim;
+    qkv_dim = (c.n_q_heads + 2 * c.n_kv_heads) * kHeadDim;
+    max_pages = (c.max_position + kPageTokens - 1) / kPageTokens + 1;
+    t_max = std::max(c.max_prefill_tokens, c.max_slots);
+    logit_rows = std::min(std::max(c.logit_chunk_rows, 1), std::max(c.max_slots, 1));
+    q_tile = attn_prefill_q_tile(c.n_q_heads, c.n_kv_heads);
+    num_pages = c.num_pages;
+    layer_stride = static_cast<size_t>(num_pages) * c.n_kv_heads * 2 * kTileElems;
+    SB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    const size_t T = t_max, S = c.max_slots + 2;  // +prefix slot, +dummy slot
+    if (dmalloc(&x, T * c.d_model) || dmalloc(&h, T * c.d_model) || dmalloc(&qkv, T * qkv_dim) ||
+        dmalloc(&attn, T * q_dim) || dmalloc(&act, T * c.d_ff) ||
+        dmalloc(&hl, static_cast<size_t>(c.max_slots) * c.d_model) ||
+        dmalloc(&hn, static_cast<size_t>(c.max_slots) * c.d_model) ||
+        dmalloc(&kv_pool, layer_stride * c.n_layers) ||
+        dmalloc(&tok_ids, T) || dmalloc(&tok_pos, T) || dmalloc(&tok_slot, T) ||
+        dmalloc(&ctx_len, S) || dmalloc(&row_slot, S) || dmalloc(&last_idx, S) ||
+        dmalloc(&page_table, S * max_pages) || dmalloc(&slot_state, S) || dmalloc(&slot_ngen, S) ||
+        dmalloc(&slot_next_tok, S) || dmalloc(&slot_pos, S) || dmalloc(&slot_done, S) ||
+        dmalloc(&slot_row, S) || dmalloc(&slot_maxnew, S))
+      return -1;
+    if (c.embedding_model) {
+      if (dmalloc(&embed_tmp, static_cast<size_t>(c.max_slots) * c.d_model)) return -1;
+    } else {
+      if (dmalloc(&logits, static_cast<size_t>(logit_rows) * c.vocab)) return -1;
+    }
+    // K/V tiles must hold finite values everywhere (masked P * V must stay 0).
+    SB_CUDA_CHECK(cudaMemsetAsync(kv_pool, 0, layer_stride * c.n_layers * sizeof(bf16), stream));
+    SB_CUDA_CHECK(cudaMemsetAsync(page_table, 0, S * max_pages * sizeof(int32_t), stream));
+    SB_CUDA_CHECK(cudaMemsetAsync(slot_done, 0, S * sizeof(int32_t), stream));
+    stage_cap = (sizeof(SeqInit) / 4) * S + static_cast<size_t>(S) * max_pages + 2 * (T / 16 + S) +
+                4 * S + 64;
+    SB_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_stage), stage_cap * 4));
+    if (dmalloc(&d_stage, stage_cap)) return -1;
+    SB_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_done), S * 4));
+    free_pages.reserve(num_pages);
+    for (int64_t p = num_pages - 1; p >= 0; --p) free_pages.push_back(static_cast<int32_t>(p));
+    SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  // ---- one pass of the transformer stack over T flattened tokens -----------
+  // prefill: attention over (cached prefix | new tokens) per sequence;
+  // decode : one token per sequence against its paged history.
+  int forward(int T, bool prefill, int n_seq, const int32_t* d_work, int n_work,
+              const int32_t* d_seq_slot, const int32_t* d_seq_q_start, const int32_t* d_seq_q_len,
+              const int32_t* d_seq_past) {
+    const auto& c = cfg;
+    const float scale = 1.0f / sqrtf(static_cast<float>(kHeadDim));
+    if (embed_gather(tok_ids, w.embed, x, T, c.d_model, stream)) return -1;
+    for (int l = 0; l < c.n_layers; ++l) {
+      if (rmsnorm(x, ln1[l], h, T, c.d_model, c.rms_eps, stream)) return -1;
+      if (gemm_bf16_tn(h, t_max, wqkv[l], qkv, nullptr, T, qkv_dim, c.d_model, qkv_dim,
+                       EPI_STORE_BF16, 0, stream))
+        return -1;
+      if (rope_kv_write(qkv, qn[l], kn[l], w.rope_cos, w.rope_sin, tok_slot, tok_pos, page_table,
+                        max_pages, kv_layer(l), T, c.n_q_heads, c.n_kv_heads, c.rms_eps, stream))
+        return -1;
+      if (prefill) {
+        if (attn_prefill(qkv, attn, kv_layer(l), page_table, max_pages, d_work, n_work, d_seq_slot,
+                         d_seq_q_start, d_seq_q_len, d_seq_past, c.n_q_heads, c.n_kv_heads, scale,
+                         stream))
+          return -1;
+      } else {
+        if (attn_decode(qkv, attn, kv_layer(l), page_table, max_pages, row_slot, ctx_len, T,
+                        c.n_q_heads, c.n_kv_heads, scale, stream))
+          return -1;
+      }
+      if (gemm_bf16_tn(attn, t_max, wo[l], x, x, T, c.d_model, q_dim, c.d_model,
+                       EPI_RESIDUAL_BF16, 0, stream))
+        return -1;
+      if (rmsnorm(x, ln2[l], h, T, c.d_model, c.rms_eps, stream)) return -1;
+      if (gemm_bf16_tn(h, t_max, wgu[l], act, nullptr, T, 2 * c.d_ff, c.d_model, c.d_ff,
+                       EPI_SWIGLU_BF16, 0, stream))
+        return -1;
+      if (gemm_bf16_tn(act, t_max, wd[l], x, x, T, c.d_model, c.d_ff, c.d_model,
+                       EPI_RESIDUAL_BF16, 0, stream))
+        return -1;
+    }
+    (void)n_seq;
+    return 0;
+  }
+
+  // final norm + lm_head + masked greedy sampling for `n` rows whose hidden
+  // states are rows idx[0..n) of x (idx == nullptr: rows 0..n).
+  int head_and_sample(int n, const int32_t* idx, const int32_t* d_row_slot,
+                      const sb200_job& job, bool has_fsm) {
+    const auto& c = cfg;
+    const bf16* src = x;
+    if (idx) {
+      if (gather_rows(idx, x, hl, n, c.d_model, stream)) return -1;
+      src = hl;
+    }
+    if (rmsnorm(src, w.final_norm, hn, n, c.d_model, c.rms_eps, stream)) return -1;
+    for (int r0 = 0; r0 < n; r0 += logit_rows) {
+      const int nr = std::min(logit_rows, n - r0);
+      if (gemm_bf16_tn(hn + static_cast<size_t>(r0) * c.d_model, c.max_slots - r0, w.lm_head,
+                       logits, nullptr,
+                       nr, c.vocab, c.d_model, c.vocab, EPI_STORE_F32, 0, stream))
+        return -1;
+      SampleArgs a{};
+      a.logits = logits;
+      a.ldl = c.vocab;
+      a.vocab = c.vocab;
+      a.B = nr;
+      a.row_slot = d_row_slot + r0;
+      a.slot_state = slot_state;
+      a.slot_ngen = slot_ngen;
+      a.slot_next_tok = slot_next_tok;
+      a.slot_pos = slot_pos;
+      a.slot_done = slot_done;
+      a.slot_row = slot_row;
+      a.slot_maxnew = slot_maxnew;
+      a.out_tokens = job.out_tokens_dev;
+      a.out_len = job.out_len_dev;
+      a.out_stride = job.max_new_tokens;
+      a.mask_bits = has_fsm ? d_mask_bits : nullptr;
+      a.mask_words = mask_words;
+      a.fsm_trans = d_fsm_trans;
+      a.fsm_accept = d_fsm_accept;
+      a.fsm_final = d_fsm_final;
+      a.tok_bytes = d_tok_bytes;
+      a.tok_off = d_tok_off;
+      a.eos_id = c.eos_id;
+      a.ignore_eos = job.ignore_eos;
+      if (sample_greedy(a, stream)) return -1;
+    }
+    return 0;
+  }
+
+  int upload_fsm(const sb200_job& job) {
+    const size_t n = job.fsm_states;
+    if (!d_tok_bytes) {
+      set_last_error("engine: output_schema given but no vocabulary bytes were set");
+      return -1;
+    }
+    mask_words = (cfg.vocab + 31) / 32;
+    if (n > fsm_cap_states) {
+      cudaFree(d_fsm_trans);
+      cudaFree(d_fsm_accept);
+      cudaFree(d_fsm_final);
+      cudaFree(d_mask_bits);
+      d_fsm_trans = nullptr, d_fsm_accept = nullptr, d_fsm_final = nullptr, d_mask_bits = nullptr;
+      fsm_cap_states = 0;
+      if (dmalloc(&d_fsm_trans, n * 256) || dmalloc(&d_fsm_accept, n) || dmalloc(&d_fsm_final, n) ||
+          dmalloc(&d_mask_bits, n * mask_words))
+        return -1;
+      fsm_cap_states = n;
+    }
+    SB_CUDA_CHECK(cudaMemcpyAsync(d_fsm_trans, job.fsm_trans, n * 256 * 4, cudaMemcpyHostToDevice,
+                                  stream));
+    SB_CUDA_CHECK(cudaMemcpyAsync(d_fsm_accept, job.fsm_accept, n, cudaMemcpyHostToDevice, stream));
+    SB_CUDA_CHECK(cudaMemcpyAsync(d_fsm_final, job.fsm_final, n, cudaMemcpyHostToDevice, stream));
+    return fsm_build_mask(d_fsm_trans, d_fsm_accept, static_cast<int>(n), d_tok_bytes, d_tok_off,
+                          cfg.vocab, cfg.eos_id, d_mask_bits, mask_words, stream);
+  }
+
+  int run(const sb200_job& job, sb200_job_stats* stats);
+};
+
+// ---------------------------------------------------------------------------
+// the scheduling loop
+// ---------------------------------------------------------------------------
+int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
+  const auto& c = cfg;
+  const int64_t N = job.n_rows;
+  const bool embed_mode = c.embedding_model != 0;
+  const bool has_fsm = !embed_mode && job.fsm_states > 0;
+  const int max_new = embed_mode ? 0 : job.max_new_tokens;
+  if (N <= 0) return 0;
+  if (!embed_mode && max_new <= 0) {
+    set_last_error("engine: max_new_tokens must be positive");
+    return -1;
+  }
+  if (embed_mode ? job.out_embed_dev == nullptr
+                 : (job.out_tokens_dev == nullptr || job.out_len_dev == nullptr)) {
+    set_last_error("engine: output buffers missing");
+    return -1;
+  }
+  const int n_prefix = job.n_prefix, n_suffix = job.n_suffix;
+  const int ctx_budget = c.max_position - max_new;  // prompt tokens that fit
+  if (n_prefix + n_suffix + 1 > ctx_budget) {
+    set_last_error("engine: system prompt + template (%d tokens) leave no room in the %d-token "
+                   "context window", n_prefix + n_suffix, c.max_position);
+    return -1;
+  }
+  // prompt pieces -> device
+  if (n_prefix > prefix_cap) {
+    cudaFree(d_prefix);
+    d_prefix = nullptr;
+    if (dmalloc(&d_prefix, static_cast<size_t>(n_prefix))) return -1;
+    prefix_cap = n_prefix;
+  }
+  if (n_suffix > suffix_cap) {
+    cudaFree(d_suffix);
+    d_suffix = nullptr;
+    if (dmalloc(&d_suffix, static_cast<size_t>(n_suffix))) return -1;
+    suffix_cap = n_suffix;
+  }
+  if (n_prefix)
+    SB_CUDA_CHECK(cudaMemcpyAsync(d_prefix, job.prefix_tokens, n_prefix * 4ull,
+                                  cudaMemcpyHostToDevice, stream));
+  if (n_suffix)
+    SB_CUDA_CHECK(cudaMemcpyAsync(d_suffix, job.suffix_tokens, n_suffix * 4ull,
+                                  cudaMemcpyHostToDevice, stream));
+  if (has_fsm && upload_fsm(job)) return -1;
+  if (!embed_mode)
+    SB_CUDA_CHECK(cudaMemsetAsync(job.out_len_dev, 0, N * sizeof(int32_t), stream));
+
+  // per-row prompt lengths (host)
+  const int64_t* roff = job.row_tok_off;
+  std::vector<int32_t> n_row_tok(N);
+  int64_t n_truncated = 0;
+  for (int64_t r = 0; r < N; ++r) {
+    int64_t n = roff[r + 1] - roff[r];
+    const int64_t room = ctx_budget - n_prefix - n_suffix;
+    if (n > room) {
+      if (!job.truncate_rows) {
+        set_last_error("engine: row %lld has %lld tokens but only %lld fit the context window "
+                       "(truncate_rows=False)", (long long)r, (long long)n, (long long)room);
+        return -1;
+      }
+      n = room;
+      ++n_truncated;
+    }
+    n_row_tok[r] = static_cast<int32_t>(n);
+  }
+
+  // staging layout (int32 units)
+  const int S = c.max_slots;
+  const int prefix_slot = S, dummy_slot = S + 1;
+  SeqInit* h_seqs = reinterpret_cast<SeqInit*>(h_stage);
+  const size_t seq_words = (sizeof(SeqInit) / 4) * (S + 2);
+  int32_t* h_pt = h_stage + seq_words;
+  int32_t* h_work = h_pt + static_cast<size_t>(S + 2) * max_pages;
+  int32_t* h_misc = h_work + 2 * (t_max / 16 + S + 2);  // seq_slot|q_start|q_len|past : 4*(S+2)
+  const SeqInit* d_seqs = reinterpret_cast<const SeqInit*>(d_stage);
+  const int32_t* d_pt = d_stage + seq_words;
+  const int32_t* d_work = d_pt + static_cast<size_t>(S + 2) * max_pages;
+  const int32_t* d_misc = d_work + 2 * (t_max / 16 + S + 2);
+
+  std::vector<int32_t> prefix_pages;
+  std::vector<std::vector<int32_t>> slot_pages(S);
+  std::vector<int32_t> free_slots;
+  for (int s = S - 1; s >= 0; --s) free_slots.push_back(s);
+  std::vector<int32_t> active;  // slots in the decode batch
+  std::vector<uint8_t> slot_live(S, 0);
+
+  auto release_all = [&]() {
+    for (auto& v : slot_pages) {
+      for (int32_t p : v) free_pages.push_back(p);
+      v.clear();
+    }
+    for (int32_t p : prefix_pages) free_pages.push_back(p);
+    prefix_pages.clear();
+  };
+
+  // Launch one prefill step for seqs h_seqs[0..n) (page rows in h_pt), T tokens total.
+  auto run_prefill = [&](int n, int T, bool sample) -> int {
+    int n_work = 0;
+    for (int i = 0; i < n; ++i) {
+      h_misc[i] = h_seqs[i].slot;
+      h_misc[(S + 2) + i] = h_seqs[i].q_start;
+      h_misc[2 * (S + 2) + i] = h_seqs[i].q_len;
+      h_misc[3 * (S + 2) + i] = h_seqs[i].past;
+      for (int t0 = 0; t0 < h_seqs[i].q_len; t0 += q_tile) {
+        h_work[2 * n_work] = i;
+        h_work[2 * n_work + 1] = t0;
+        ++n_work;
+      }
+    }
+    SB_CUDA_CHECK(cudaMemcpyAsync(d_stage, h_stage, stage_cap * 4, cudaMemcpyHostToDevice, stream));
+    init_slots_kernel<<<n, 128, 0, stream>>>(d_seqs, d_pt, max_pages, page_table, slot_state,
+                                             slot_ngen, slot_pos, slot_done, slot_row, slot_maxnew,
+                                             slot_next_tok);
+    prefill_prepare_kernel<<<n, 128, 0, stream>>>(d_seqs, d_prefix, n_prefix, d_suffix, n_suffix,
+                                                  job.row_tokens_dev, job.row_tok_off_dev, tok_ids,
+                                                  tok_pos, tok_slot, last_idx);
+    SB_CUDA_CHECK(cudaGetLastError());
+    if (forward(T, true, n, d_work, n_work, d_misc, d_misc + (S + 2), d_misc + 2 * (S + 2),
+                d_misc + 3 * (S + 2)))
+      return -1;
+    if (!sample) return 0;
+    if (embed_mode) {
+      if (gather_rows(last_idx, x, hl, n, c.d_model, stream)) return -1;
+      if (rmsnorm(hl, w.final_norm, hn, n, c.d_model, c.rms_eps, stream)) return -1;
+      if (l2_normalize_rows(hn, embed_tmp, n, c.d_model, stream)) return -1;
+      scatter_embed_kernel<<<n, 128, 0, stream>>>(embed_tmp, d_seqs, job.out_embed_dev, c.d_model);
+      SB_CUDA_CHECK(cudaGetLastError());
+      return 0;
+    }
+    return head_and_sample(n, last_idx, d_misc /* seq_slot */, job, has_fsm);
+  };
+
+  // ---- shared prefix: compute its KV once, every row's page table points at it ----
+  const int prefix_cached = (job.share_prefix && n_prefix >= kPageTokens)
+                                ? (n_prefix / kPageTokens) * kPageTokens
+                                : 0;
+  if (prefix_cached > 0) {
+    if (prefix_cached > c.max_prefill_tokens) {
+      set_last_error("engine: shared prefix (%d tokens) exceeds max_prefill_tokens", prefix_cached);
+      return -1;
+    }
+    const int np = prefix_cached / kPageTokens;
+    if (static_cast<int64_t>(free_pages.size()) < np) {
+      set_last_error("engine: KV pool too small for the shared prefix");
+      return -1;
+    }
+    for (int i = 0; i < np; ++i) {
+      prefix_pages.push_back(free_pages.back());
+      free_pages.pop_back();
+    }
+    h_seqs[0] = SeqInit{prefix_slot, -1, 0, prefix_cached, 0, 0, 1, -1};
+    std::fill(h_pt, h_pt + max_pages, 0);
+    std::copy(prefix_pages.begin(), prefix_pages.end(), h_pt);
+    if (run_prefill(1, prefix_cached, false)) {
+      release_all();
+      return -1;
+    }
+    SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+
+  int64_t next_row = 0, rows_done = 0, in_tokens = 0, steps_prefill = 0, steps_decode = 0;
+  int64_t decode_tokens = 0, prefill_tokens = prefix_cached;
+  const int pages_shared = prefix_cached / kPageTokens;
+  int rc = 0;
+
+  auto admit = [&]() -> int {  // returns number of rows admitted, <0 on error
+    int n = 0, T = 0;
+    while (next_row < N && !free_slots.empty() && n < S) {
+      const int64_t r = next_row;
+      const int P = n_prefix + n_row_tok[r] + n_suffix;
+      if (P <= 0) {
+        set_last_error("engine: row %lld renders to an empty prompt", (long long)r);
+        return -1;
+      }
+      const int past = std::min(prefix_cached, ((P - 1) / kPageTokens) * kPageTokens);
+      const int q_len = P - past;
+      if (T + q_len > c.max_prefill_tokens) {
+        if (n == 0) {
+          set_last_error("engine: row %lld needs %d prefill tokens > max_prefill_tokens=%d",
+                         (long long)r, q_len, c.max_prefill_tokens);
+          return -1;
+        }
+        break;
+      }
+      const int total_pages = (P + max_new + kPageTokens - 1) / kPageTokens;
+      const int own = total_pages - past / kPageTokens;
+      if (static_cast<int64_t>(free_pages.size()) < own) {
+        if (n == 0 && active.empty()) {
+          set_last_error("engine: KV pool (%lld pages) cannot hold one row of %d tokens",
+                         (long long)num_pages, P + max_new);
+          return -1;
+        }
+        break;
+      }
+      const int slot = free_slots.back();
+      free_slots.pop_back();
+      int32_t* pt = h_pt + static_cast<size_t>(n) * max_pages;
+      std::fill(pt, pt + max_pages, 0);
+      for (int i = 0; i < past / kPageTokens; ++i) pt[i] = prefix_pages[i];
+      auto& mine = slot_pages[slot];
+      for (int i = 0; i < own; ++i) {
+        mine.push_back(free_pages.back());
+        pt[past / kPageTokens + i] = free_pages.back();
+        free_pages.pop_back();
+      }
+      h_seqs[n] = SeqInit{slot, static_cast<int32_t>(r), T, q_len, past, n_row_tok[r], max_new,
+                          has_fsm ? job.fsm_start : -1};
+      slot_live[slot] = 1;
+      T += q_len;
+      in_tokens += P;
+      ++n;
+      ++next_row;
+    }
+    if (n == 0) return 0;
+    if (run_prefill(n, T, true)) return -1;
+    prefill_tokens += T;
+    ++steps_prefill;
+    for (int i = 0; i < n; ++i) active.push_back(h_seqs[i].slot);
+    return n;
+  };
+
+  auto retire = [&]() -> int {  // reads the done flags, frees finished slots
+    SB_CUDA_CHECK(cudaMemcpyAsync(h_done, slot_done, (S + 2) * 4ull, cudaMemcpyDeviceToHost, stream));
+    SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    size_t k = 0;
+    for (size_t i = 0; i < active.size(); ++i) {
+      const int s = active[i];
+      if (h_done[s]) {
+        for (int32_t p : slot_pages[s]) free_pages.push_back(p);
+        slot_pages[s].clear();
+        slot_live[s] = 0;
+        free_slots.push_back(s);
+        ++rows_done;
+      } else {
+        active[k++] = s;
+      }
+    }
+    active.resize(k);
+    return 0;
+  };
+  (void)pages_shared;
+  (void)dummy_slot;
+
+  const int min_admit = std::max(1, c.min_admit_rows);
+  while (rows_done < N) {
+    // ---- admission: refill free slots with new rows (their prefill) ----
+    const bool can_admit = next_row < N && !free_slots.empty();
+    if (can_admit && (active.empty() || static_cast<int>(free_slots.size()) >= min_admit ||
+                      N - next_row <= static_cast<int64_t>(free_slots.size()))) {
+      const int n = admit();
+      if (n < 0) {
+        rc = -1;
+        break;
+      }
+      if (embed_mode) {
+        // prefill-only: rows are complete, recycle their slots right away
+        SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+        for (int s : active) {
+          for (int32_t p : slot_pages[s]) free_pages.push_back(p);
+          slot_pages[s].clear();
+          free_slots.push_back(s);
+          ++rows_done;
+        }
+        active.clear();
+        if (job.progress) job.progress(rows_done, in_tokens, 0, job.progress_user);
+        continue;
+      }
+      if (n > 0) {
+        if (retire()) {
+          rc = -1;
+          break;
+        }
+        if (job.progress) job.progress(rows_done, in_tokens, decode_tokens, job.progress_user);
+        continue;  // try to admit more before decoding
+      }
+    }
+    if (active.empty()) {
+      if (next_row >= N) break;
+      set_last_error("engine: scheduler stalled (no active rows, none admissible)");
+      rc = -1;
+      break;
+    }
+    // ---- one decode step over all active rows ----
+    const int B = static_cast<int>(active.size());
+    std::copy(active.begin(), active.end(), h_misc);
+    SB_CUDA_CHECK(cudaMemcpyAsync(row_slot, h_misc, B * 4ull, cudaMemcpyHostToDevice, stream));
+    if (prepare_decode(row_slot, slot_next_tok, slot_pos, tok_ids, tok_pos, tok_slot, ctx_len, B,
+                       stream) ||
+        forward(B, false, B, nullptr, 0, nullptr, nullptr, nullptr, nullptr) ||
+        head_and_sample(B, nullptr, row_slot, job, has_fsm)) {
+      rc = -1;
+      break;
+    }
+    decode_tokens += B;
+    ++steps_decode;
+    if (retire()) {
+      rc = -1;
+      break;
+    }
+    if (job.progress && (steps_decode % 8 == 0 || rows_done == N))
+      job.progress(rows_done, in_tokens, decode_tokens, job.progress_user);
+  }
+  cudaStreamSynchronize(stream);
+  release_all();
+  if (stats) {
+    stats->rows_done = rows_done;
+    stats->input_tokens = in_tokens;
+    stats->prefill_tokens = prefill_tokens;
+    stats->decode_tokens = decode_tokens;
+    stats->prefill_steps = steps_prefill;
+    stats->decode_steps = steps_decode;
+    stats->rows_truncated = n_truncated;
+    stats->prefix_cached_tokens = prefix_cached;
+  }
+  if (rc == 0) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_last_error("engine: CUDA error after run: %s", cudaGetErrorString(e));
+      rc = -1;
+    }
+  }
+  return rc;
+}
+
+}  // namespace sb
+
+// ---------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------
+using namespace sb;
+
+extern "C" {
+
+int sb200_engine_create(const sb200_engine_config* cfg, const sb200_engine_weights* w, void** out) {
+  *out = nullptr;
+  if (!cfg || !w) {
+    set_last_error("engine_create: null config/weights");
+    return -1;
+  }
+  if (cfg->n_q_heads % cfg->n_kv_heads != 0 || cfg->d_model % 64 != 0 || cfg->d_ff % 64 != 0 ||
+      cfg->vocab % 32 != 0 || cfg->max_slots <= 0 || cfg->max_prefill_tokens < 16 ||
+      cfg->num_pages <= 0) {
+    set_last_error("engine_create: unsupported geometry (d_model/d_ff %% 64, vocab %% 32, ...)");
+    return -1;
+  }
+  auto* e = new Engine();
+  e->cfg = *cfg;
+  e->w = *w;
+  const int L = cfg->n_layers;
+  auto cp = [&](std::vector<const void*>& v, const void* const* src, bool optional) {
+    v.assign(L, nullptr);
+    if (src)
+      for (int i = 0; i < L; ++i) v[i] = src[i];
+    (void)optional;
+  };
+  cp(e->ln1, w->ln1, false);
+  cp(e->ln2, w->ln2, false);
+  cp(e->wqkv, w->wqkv, false);
+  cp(e->wo, w->wo, false);
+  cp(e->wgu, w->wgu, false);
+  cp(e->wd, w->wd, false);
+  cp(e->qn, cfg->qk_norm ? w->q_norm : nullptr, true);
+  cp(e->kn, cfg->qk_norm ? w->k_norm : nullptr, true);
+  for (int i = 0; i < L; ++i) {
+    if (!e->ln1[i] || !e->ln2[i] || !e->wqkv[i] || !e->wo[i] || !e->wgu[i] || !e->wd[i] ||
+        (cfg->qk_norm && (!e->qn[i] || !e->kn[i]))) {
+      set_last_error("engine_create: missing weight pointer in layer %d", i);
+      delete e;
+      return -1;
+    }
+  }
+  if (e->init()) {
+    delete e;
+    return -1;
+  }
+  *out = e;
+  return 0;
+}
+
+void sb200_engine_destroy(void* engine) { delete static_cast<Engine*>(engine); }
+
+int sb200_engine_set_vocab(void* engine, const uint8_t* tok_bytes, const int32_t* tok_off) {
+  auto* e = static_cast<Engine*>(engine);
+  const int V = e->cfg.vocab;
+  cudaFree(e->d_tok_bytes);
+  cudaFree(e->d_tok_off);
+  e->d_tok_bytes = nullptr, e->d_tok_off = nullptr;
+  const size_t nb = tok_off[V] > 0 ? tok_off[V] : 1;
+  SB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&e->d_tok_bytes), nb));
+  SB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&e->d_tok_off), (V + 1) * 4ull));
+  SB_CUDA_CHECK(cudaMemcpy(e->d_tok_bytes, tok_bytes, tok_off[V], cudaMemcpyHostToDevice));
+  SB_CUDA_CHECK(cudaMemcpy(e->d_tok_off, tok_off, (V + 1) * 4ull, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int sb200_engine_run(void* engine, const sb200_job* job, sb200_job_stats* stats) {
+  if (!engine || !job) {
+    set_last_error("engine_run: null argument");
+    return -1;
+  }
+  return static_cast<Engine*>(engine)->run(*job, stats);
+}
+
+void* sb200_engine_stream(void* engine) { return static_cast<Engine*>(engine)->stream; }
+
+}  // extern "C"

@@ -1,0 +1,379 @@
+"""Python host for the engine-level C-ABI (include/sutro_b200.h).
+
+`LocalEngine` is one model replica on one GPU: weights (PyTorch tensors, only as
+storage), the GPU tokenizer, and the C++ scheduler.  `LocalEngine.generate()` is the
+whole hot path for a list of rows: encode -> H2D -> tokenize -> prefill/decode with
+optional schema mask -> detokenize -> D2H.  No step runs on the CPU; if the shared
+library or a CUDA device is missing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import modelspec as MS
+from . import vocab as VB
+from .schema_fsm import ByteDFA, FsmLimits, compile_schema
+from .unicode_tables import class_table
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+c_vpp = C.POINTER(C.c_void_p)
+
+
+class EngineConfigC(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n_layers", "d_model", "n_q_heads", "n_kv_heads", "d_ff",
+                                       "vocab", "max_position")] + \
+               [("rms_eps", C.c_float), ("qk_norm", C.c_int), ("embedding_model", C.c_int),
+                ("eos_id", C.c_int), ("max_slots", C.c_int), ("max_prefill_tokens", C.c_int),
+                ("logit_chunk_rows", C.c_int), ("min_admit_rows", C.c_int),
+                ("num_pages", C.c_int64)]
+
+
+class EngineWeightsC(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("embed", "lm_head", "final_norm", "rope_cos",
+                                          "rope_sin")] + \
+               [(n, c_vpp) for n in ("ln1", "ln2", "wqkv", "wo", "wgu", "wd", "q_norm", "k_norm")]
+
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_int64, C.c_int64, C.c_int64, C.c_void_p)
+
+
+class JobC(C.Structure):
+    _fields_ = [("row_tokens_dev", C.c_void_p), ("row_tok_off_dev", C.c_void_p),
+                ("row_tok_off", c_i64p), ("n_rows", C.c_int64),
+                ("prefix_tokens", c_i32p), ("n_prefix", C.c_int),
+                ("suffix_tokens", c_i32p), ("n_suffix", C.c_int),
+                ("share_prefix", C.c_int), ("max_new_tokens", C.c_int), ("ignore_eos", C.c_int),
+                ("truncate_rows", C.c_int),
+                ("fsm_trans", c_i32p), ("fsm_accept", c_u8p), ("fsm_final", c_u8p),
+                ("fsm_states", C.c_int), ("fsm_start", C.c_int),
+                ("out_tokens_dev", C.c_void_p), ("out_len_dev", C.c_void_p),
+                ("out_embed_dev", C.c_void_p),
+                ("progress", PROGRESS_FN), ("progress_user", C.c_void_p)]
+
+
+class JobStatsC(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("rows_done", "input_tokens", "prefill_tokens",
+                                         "decode_tokens", "prefill_steps", "decode_steps",
+                                         "rows_truncated", "prefix_cached_tokens")]
+
+
+L.register("sb200_engine_create", C.c_int, [C.POINTER(EngineConfigC), C.POINTER(EngineWeightsC),
+                                            C.POINTER(C.c_void_p)])
+L.register("sb200_engine_destroy", None, [C.c_void_p])
+L.register("sb200_engine_set_vocab", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p])
+L.register("sb200_engine_run", C.c_int, [C.c_void_p, C.POINTER(JobC), C.POINTER(JobStatsC)])
+L.register("sb200_engine_stream", C.c_void_p, [C.c_void_p])
+L.register("sb200_tokenizer_create", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.POINTER(C.c_void_p)])
+L.register("sb200_tokenizer_destroy", None, [C.c_void_p])
+L.register("sb200_tokenizer_encode", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                               C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p])
+L.register("sb200_tokenizer_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                               C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p])
+
+
+def _np_ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+# --------------------------------------------------------------------------- Arrow-style text
+def rows_to_blob(rows) -> Tuple[np.ndarray, np.ndarray]:
+    """list[str] / pyarrow array / pandas Series -> (uint8 blob, int64 offsets[n+1]).
+    None becomes the empty string (the reference maps nulls to "" when concatenating
+    columns, sutro/common.py:83,97)."""
+    import pyarrow as pa
+    if isinstance(rows, (pa.Array, pa.ChunkedArray)):
+        arr = rows
+    else:
+        arr = pa.array(["" if r is None else (r if isinstance(r, str) else str(r)) for r in rows]
+                       if not _all_str(rows) else rows, type=pa.large_string())
+    if isinstance(arr, pa.ChunkedArray):
+        arr = arr.combine_chunks()
+    if arr.type != pa.large_string():
+        arr = arr.cast(pa.large_string())
+    if arr.null_count:
+        arr = arr.fill_null("")
+    bufs = arr.buffers()
+    n = len(arr)
+    off = np.frombuffer(bufs[1], dtype=np.int64, count=n + 1, offset=arr.offset * 8)
+    data = (np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None
+            else np.zeros(0, dtype=np.uint8))
+    if off[0] != 0:
+        data = data[off[0]:off[-1]]
+        off = off - off[0]
+    else:
+        data = data[:off[-1]]
+    return data, off
+
+
+def _all_str(rows) -> bool:
+    return isinstance(rows, list) and all(isinstance(r, str) for r in rows)
+
+
+def blob_to_rows(data: np.ndarray, off: np.ndarray) -> List[str]:
+    """Decode with errors='replace': an unconstrained model may emit bytes that are not
+    UTF-8 (same policy as HF byte-level decoders)."""
+    raw = data.tobytes()
+    return [raw[off[i]:off[i + 1]].decode("utf-8", errors="replace") for i in range(len(off) - 1)]
+
+
+# --------------------------------------------------------------------------- tokenizer
+class GpuTokenizer:
+    """Byte-level BPE on the GPU (csrc/tokenizer.cu)."""
+
+    def __init__(self, v: VB.Vocab, device: torch.device):
+        self.v, self.device = v, device
+        blob, off = v.byte_blob()
+        self._blob, self._off = blob, off
+        merges = np.ascontiguousarray(v.merge_array())
+        cls = np.ascontiguousarray(class_table())
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            L.check(L.lib().sb200_tokenizer_create(
+                merges.ctypes.data, len(v.merges), None, cls.ctypes.data, v.digits,
+                blob.ctypes.data, off.ctypes.data, v.vocab_size, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                L.lib().sb200_tokenizer_destroy(self._h)
+        except Exception:  # interpreter shutdown
+            pass
+
+    def encode_blob_dev(self, data: np.ndarray, off: np.ndarray):
+        """-> (tokens[int32, device], row_tok_off[int64, device]); includes the H2D copy."""
+        dev = self.device
+        n_bytes, n_rows = int(off[-1]), len(off) - 1
+        d_text = torch.from_numpy(np.ascontiguousarray(data)).to(dev, non_blocking=False) \
+            if n_bytes else torch.zeros(1, dtype=torch.uint8, device=dev)
+        d_off = torch.from_numpy(np.ascontiguousarray(off)).to(dev)
+        d_tok = torch.empty(max(n_bytes, 1), dtype=torch.int32, device=dev)
+        d_toff = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.lib().sb200_tokenizer_encode(self._h, d_text.data_ptr(), n_bytes,
+                                                   d_off.data_ptr(), n_rows, d_tok.data_ptr(),
+                                                   d_toff.data_ptr(), L.current_stream()))
+        return d_tok, d_toff
+
+    def encode(self, texts: Sequence[str]) -> List[List[int]]:
+        data, off = rows_to_blob(list(texts))
+        d_tok, d_toff = self.encode_blob_dev(data, off)
+        toff = d_toff.cpu().numpy()
+        tok = d_tok[:int(toff[-1])].cpu().numpy()
+        return [tok[toff[i]:toff[i + 1]].tolist() for i in range(len(texts))]
+
+    def encode_pieces(self, pieces: Sequence[str]) -> List[int]:
+        """Template pieces: special-token names map to their ids, text is tokenised."""
+        text_idx = [i for i, p in enumerate(pieces) if p not in self.v.specials]
+        enc = self.encode([pieces[i] for i in text_idx]) if text_idx else []
+        out: List[int] = []
+        it = iter(enc)
+        for p in pieces:
+            out += [self.v.specials[p]] if p in self.v.specials else next(it)
+        return out
+
+    def decode_dev(self, d_tok: torch.Tensor, d_toff: torch.Tensor) -> Tuple[np.ndarray, np.ndarray]:
+        """compact tokens + row offsets (device) -> (uint8 blob, int64 offsets) on the host."""
+        dev = self.device
+        n_tok, n_rows = int(d_tok.numel()), int(d_toff.numel()) - 1
+        d_boff = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        lib = L.lib()
+        with torch.cuda.device(dev):
+            L.check(lib.sb200_tokenizer_decode(self._h, d_tok.data_ptr(), n_tok, d_toff.data_ptr(),
+                                               n_rows, None, d_boff.data_ptr(), L.current_stream()))
+            total = int(d_boff[-1].item())
+            d_bytes = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+            L.check(lib.sb200_tokenizer_decode(self._h, d_tok.data_ptr(), n_tok, d_toff.data_ptr(),
+                                               n_rows, d_bytes.data_ptr(), d_boff.data_ptr(),
+                                               L.current_stream()))
+        return d_bytes[:total].cpu().numpy(), d_boff.cpu().numpy()
+
+
+# --------------------------------------------------------------------------- engine
+@dataclass
+class GenerationResult:
+    outputs: Optional[List[str]]
+    out_tokens: Optional[List[List[int]]]
+    embeddings: Optional[np.ndarray]
+    stats: Dict[str, Any] = field(default_factory=dict)
+
+
+class LocalEngine:
+    def __init__(self, spec: MS.ModelSpec, weights: MS.EngineWeights, vocab: VB.Vocab,
+                 device: int | str | torch.device = 0, max_slots: int = 512,
+                 max_prefill_tokens: int = 8192, kv_pages: Optional[int] = None,
+                 kv_fraction: float = 0.8, logit_chunk_rows: int = 1024,
+                 min_admit_rows: Optional[int] = None):
+        if not torch.cuda.is_available():
+            raise L.Sb200Error("sutro_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.spec, self.weights, self.vocab = spec, weights, vocab
+        if vocab.vocab_size != spec.vocab_size:
+            raise ValueError("vocabulary size does not match the model")
+        self.max_slots, self.max_prefill_tokens = max_slots, max_prefill_tokens
+        with torch.cuda.device(self.device):
+            self.cos, self.sin = (t.to(self.device).contiguous() for t in MS.rope_tables(spec))
+            page_bytes = spec.kv_bytes_per_token * 16
+            if kv_pages is None:
+                free, _ = torch.cuda.mem_get_info(self.device)
+                act = max(max_prefill_tokens, max_slots) * 2 * (
+                    2 * spec.d_model + spec.qkv_dim + spec.q_dim + spec.d_ff)
+                act += min(logit_chunk_rows, max_slots) * spec.vocab_size * 4
+                kv_pages = int(max(0, (free - act) * kv_fraction) // page_bytes)
+                # never more than every slot at full context
+                kv_pages = min(kv_pages, max_slots * (spec.max_position // 16 + 1) + 64)
+            if kv_pages < 8:
+                raise L.Sb200Error("not enough device memory for a KV pool")
+            self.kv_pages = kv_pages
+            cfg = EngineConfigC(spec.n_layers, spec.d_model, spec.n_q_heads, spec.n_kv_heads,
+                                spec.d_ff, spec.vocab_size, spec.max_position, spec.rms_eps,
+                                int(spec.qk_norm), int(spec.embedding_model), vocab.eos_id,
+                                max_slots, max_prefill_tokens, logit_chunk_rows,
+                                min_admit_rows if min_admit_rows is not None
+                                else max(1, max_slots // 4), kv_pages)
+            self._keep: List[Any] = []
+
+            def arr(ts):
+                a = (C.c_void_p * spec.n_layers)(*[L.ptr(t) for t in ts])
+                self._keep.append(a)
+                return C.cast(a, c_vpp)
+
+            w = weights
+            wc = EngineWeightsC(L.ptr(w.embed), L.ptr(w.lm_head), L.ptr(w.final_norm),
+                                L.ptr(self.cos), L.ptr(self.sin), arr(w.ln1), arr(w.ln2),
+                                arr(w.wqkv), arr(w.wo), arr(w.wgu), arr(w.wd),
+                                arr(w.q_norm) if spec.qk_norm else None,
+                                arr(w.k_norm) if spec.qk_norm else None)
+            torch.cuda.synchronize(self.device)
+            h = C.c_void_p()
+            L.check(L.lib().sb200_engine_create(C.byref(cfg), C.byref(wc), C.byref(h)))
+            self._h = h
+            self.tokenizer = GpuTokenizer(vocab, self.device)
+            L.check(L.lib().sb200_engine_set_vocab(self._h, self.tokenizer._blob.ctypes.data,
+                                                   self.tokenizer._off.ctypes.data))
+        self._fsm_cache: Dict[str, ByteDFA] = {}
+        self._tpl_cache: Dict[Any, Tuple[np.ndarray, np.ndarray]] = {}
+
+    # ---- construction helpers -------------------------------------------
+    @classmethod
+    def from_seed(cls, model: str, seed: int = 0, device=0, vocab_seed: int = 0, **kw):
+        """Random-init replica of a named architecture (no checkpoints exist offline)."""
+        spec = MS.get_spec(model)
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if spec.n_params() > 50_000_000:
+            weights = MS.make_engine_weights_on_device(spec, seed, dev)
+        else:
+            weights = MS.pack_for_engine(spec, MS.make_weights(spec, seed), dev)
+        v = VB.build_vocab(spec.family, spec.vocab_size, seed=vocab_seed)
+        return cls(spec, weights, v, device=dev, **kw)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                L.lib().sb200_engine_destroy(self._h)
+        except Exception:
+            pass
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().sb200_engine_destroy(self._h)
+            self._h = None
+
+    # ---- the hot path -----------------------------------------------------
+    def _template_tokens(self, system_prompt: Optional[str]):
+        key = (system_prompt, self.spec.embedding_model)
+        if key not in self._tpl_cache:
+            tpl = (VB.embedding_template(self.spec.family) if self.spec.embedding_model
+                   else VB.chat_template(self.spec.family, system_prompt))
+            pre = np.asarray(self.tokenizer.encode_pieces(tpl.prefix), dtype=np.int32)
+            suf = np.asarray(self.tokenizer.encode_pieces(tpl.suffix), dtype=np.int32)
+            self._tpl_cache[key] = (pre, suf)
+        return self._tpl_cache[key]
+
+    def compile_schema(self, schema: Dict[str, Any], limits: Optional[FsmLimits] = None) -> ByteDFA:
+        import json
+        key = json.dumps(schema, sort_keys=True) + repr(limits)
+        if key not in self._fsm_cache:
+            self._fsm_cache[key] = compile_schema(schema, limits)
+        return self._fsm_cache[key]
+
+    def generate(self, rows, system_prompt: Optional[str] = None,
+                 json_schema: Optional[Dict[str, Any]] = None, max_new_tokens: int = 64,
+                 ignore_eos: bool = False, truncate_rows: bool = True, share_prefix: bool = True,
+                 fsm_limits: Optional[FsmLimits] = None,
+                 progress: Optional[Callable[[int, int, int], None]] = None,
+                 return_tokens: bool = False, return_text: bool = True) -> GenerationResult:
+        dev = self.device
+        t0 = time.perf_counter()
+        data, off = rows_to_blob(rows)
+        n_rows = len(off) - 1
+        pre, suf = self._template_tokens(system_prompt)
+        dfa = self.compile_schema(json_schema, fsm_limits) if json_schema is not None else None
+        t_host = time.perf_counter()
+        with torch.cuda.device(dev):
+            d_tok, d_toff = self.tokenizer.encode_blob_dev(data, off)
+            toff = d_toff.cpu().numpy()          # syncs the tokenizer stream
+            t_tok = time.perf_counter()
+            emb_mode = self.spec.embedding_model
+            d_out = d_len = d_emb = None
+            if emb_mode:
+                d_emb = torch.empty(n_rows, self.spec.d_model, dtype=torch.float32, device=dev)
+            else:
+                d_out = torch.empty(n_rows, max_new_tokens, dtype=torch.int32, device=dev)
+                d_len = torch.zeros(n_rows, dtype=torch.int32, device=dev)
+            cb = PROGRESS_FN(lambda r, i, o, u: progress(r, i, o)) if progress else PROGRESS_FN()
+            job = JobC()
+            job.row_tokens_dev, job.row_tok_off_dev = d_tok.data_ptr(), d_toff.data_ptr()
+            job.row_tok_off, job.n_rows = _np_ptr(toff, c_i64p), n_rows
+            job.prefix_tokens, job.n_prefix = _np_ptr(pre, c_i32p), len(pre)
+            job.suffix_tokens, job.n_suffix = _np_ptr(suf, c_i32p), len(suf)
+            job.share_prefix, job.max_new_tokens = int(share_prefix), max_new_tokens
+            job.ignore_eos, job.truncate_rows = int(ignore_eos), int(truncate_rows)
+            if dfa is not None:
+                job.fsm_trans = _np_ptr(dfa.trans, c_i32p)
+                job.fsm_accept = _np_ptr(dfa.accept, c_u8p)
+                job.fsm_final = _np_ptr(dfa.final, c_u8p)
+                job.fsm_states, job.fsm_start = dfa.n_states, dfa.start
+            job.out_tokens_dev = L.ptr(d_out)
+            job.out_len_dev = L.ptr(d_len)
+            job.out_embed_dev = L.ptr(d_emb)
+            job.progress = cb
+            st = JobStatsC()
+            torch.cuda.synchronize(dev)
+            L.check(L.lib().sb200_engine_run(self._h, C.byref(job), C.byref(st)))
+            t_run = time.perf_counter()
+            outputs = out_tokens = emb = None
+            n_out = 0
+            if emb_mode:
+                emb = d_emb.cpu().numpy()
+            else:
+                lens = d_len.to(torch.int64)
+                ooff = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(lens, 0, out=ooff[1:])
+                keep = torch.arange(max_new_tokens, device=dev)[None, :] < lens[:, None]
+                flat = d_out[keep].contiguous()
+                n_out = int(flat.numel())
+                if return_text:
+                    b, boff = self.tokenizer.decode_dev(flat, ooff)
+                    outputs = blob_to_rows(b, boff)
+                if return_tokens:
+                    fl, oo = flat.cpu().numpy(), ooff.cpu().numpy()
+                    out_tokens = [fl[oo[i]:oo[i + 1]].tolist() for i in range(n_rows)]
+            t_end = time.perf_counter()
+        stats = {k: int(getattr(st, k)) for k, _ in JobStatsC._fields_}
+        stats.update(output_tokens=n_out, n_rows=n_rows, h2d_bytes=int(data.nbytes + off.nbytes),
+                     t_host_prep_s=t_host - t0, t_tokenize_s=t_tok - t_host,
+                     t_engine_s=t_run - t_tok, t_detok_s=t_end - t_run, t_total_s=t_end - t0,
+                     fsm_states=0 if dfa is None else dfa.n_states)
+        return GenerationResult(outputs, out_tokens, emb, stats)
