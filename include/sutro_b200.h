@@ -165,11 +165,29 @@ typedef struct {
   float* out_embed_dev;           /* [n_rows, d_model] (embedding models)               */
   sb200_progress_fn progress;     /* may be NULL                                        */
   void* progress_user;
+  int profile;                    /* 1: time every kernel launch with CUDA events        */
 } sb200_job;
+
+/* kernel classes for the per-class launch counts / device times in sb200_job_stats */
+enum {
+  SB200_KC_GEMM = 0,
+  SB200_KC_ATTN_DECODE = 1,
+  SB200_KC_ATTN_PREFILL = 2,
+  SB200_KC_NORM = 3,
+  SB200_KC_ROPE = 4,
+  SB200_KC_SAMPLE = 5,
+  SB200_KC_EMBED = 6,
+  SB200_KC_OTHER = 7,
+  SB200_KC_COUNT = 8
+};
 
 typedef struct {
   int64_t rows_done, input_tokens, prefill_tokens, decode_tokens;
   int64_t prefill_steps, decode_steps, rows_truncated, prefix_cached_tokens;
+  int64_t kernel_launches[SB200_KC_COUNT]; /* always filled                              */
+  double kernel_ms[SB200_KC_COUNT];        /* device time per class (job.profile only)    */
+  double gemm_flops;                       /* 2*M*N*K summed over every GEMM launch       */
+  double attn_decode_bytes;                /* K/V bytes the decode attention had to read  */
 } sb200_job_stats;
 
 int sb200_engine_create(const sb200_engine_config* cfg, const sb200_engine_weights* w, void** out);

@@ -68,7 +68,7 @@ class GenResult:
     margins: List[float]        # top1 - top2 logit among allowed tokens, one per decision
                                 # (len(tokens), +1 when the last decision was EOS)
     finished_by: str            # "eos" | "fsm" | "length"
-    final_hidden: Optional[torch.Tensor] = None
+    runner_up: Optional[List[int]] = None   # second-best allowed token at each decision
 
 
 class RefModel:
@@ -152,6 +152,7 @@ class RefModel:
         h = self._forward(prompt, 0, cache)[-1:]
         out: List[int] = []
         margins: List[float] = []
+        second: List[int] = []
         state = fsm.start if fsm is not None else None
         pos = len(prompt)
         why = "length"
@@ -165,6 +166,7 @@ class RefModel:
             best = top.values[0]
             tok = int((lg == best).nonzero()[0])
             margins.append(float(top.values[0] - top.values[1]))
+            second.append(int(top.indices[1]) if int(top.indices[0]) == tok else int(top.indices[0]))
             if tok == eos_id and not ignore_eos:
                 why = "eos"
                 break
@@ -178,4 +180,4 @@ class RefModel:
                 break
             h = self._forward([tok], pos, cache)
             pos += 1
-        return GenResult(out, margins, why)
+        return GenResult(out, margins, why, second)

@@ -85,6 +85,60 @@ __global__ void scatter_embed_kernel(const float* __restrict__ src, const SeqIni
     dst[static_cast<size_t>(row) * d + i] = src[static_cast<size_t>(blockIdx.x) * d + i];
 }
 
+// Per-kernel-class device timing (job.profile): CUDA events around every launch on the
+// engine stream, resolved after the job.  Used by bench.py for the roofline numbers.
+struct Profiler {
+  bool on = false;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  std::vector<std::pair<int, size_t>> spans;
+  double ms[SB200_KC_COUNT] = {0};
+  int64_t launches[SB200_KC_COUNT] = {0};
+  void reset(bool enable, cudaStream_t s) {
+    on = enable;
+    stream = s;
+    used = 0;
+    spans.clear();
+    for (int i = 0; i < SB200_KC_COUNT; ++i) ms[i] = 0, launches[i] = 0;
+  }
+  void begin(int cls) {
+    ++launches[cls];
+    if (!on) return;
+    while (pool.size() < used + 2) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    cudaEventRecord(pool[used], stream);
+    spans.emplace_back(cls, used);
+  }
+  void end() {
+    if (!on) return;
+    cudaEventRecord(pool[used + 1], stream);
+    used += 2;
+  }
+  void resolve() {
+    if (!on) return;
+    cudaStreamSynchronize(stream);
+    for (auto& sp : spans) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, pool[sp.second], pool[sp.second + 1]);
+      ms[sp.first] += t;
+    }
+  }
+  ~Profiler() {
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+#define SB_K(cls, call)        \
+  do {                         \
+    prof.begin(cls);           \
+    const int _rc = (call);    \
+    prof.end();                \
+    if (_rc) return -1;        \
+  } while (0)
+
 template <typename T>
 int dmalloc(T** p, size_t n) {
   SB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
@@ -126,6 +180,9 @@ struct Engine {
   int prefix_cap = 0, suffix_cap = 0;
   // host page allocator
   std::vector<int32_t> free_pages;
+  Profiler prof;
+  double gemm_flops = 0, attn_decode_bytes = 0;
+  int device = 0;
 
   ~Engine() {
     for (void* p : {(void*)x, (void*)h, (void*)qkv, (void*)attn, (void*)act, (void*)hl, (void*)hn,
@@ -154,6 +211,7 @@ struct Engine {
     q_tile = attn_prefill_q_tile(c.n_q_heads, c.n_kv_heads);
     num_pages = c.num_pages;
     layer_stride = static_cast<size_t>(num_pages) * c.n_kv_heads * 2 * kTileElems;
+    SB_CUDA_CHECK(cudaGetDevice(&device));
     SB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     const size_t T = t_max, S = c.max_slots + 2;  // +prefix slot, +dummy slot
     if (dmalloc(&x, T * c.d_model) || dmalloc(&h, T * c.d_model) || dmalloc(&qkv, T * qkv_dim) ||
@@ -195,35 +253,36 @@ struct Engine {
               const int32_t* d_seq_past) {
     const auto& c = cfg;
     const float scale = 1.0f / sqrtf(static_cast<float>(kHeadDim));
-    if (embed_gather(tok_ids, w.embed, x, T, c.d_model, stream)) return -1;
+    auto gemm = [&](const void* a, const void* wt, void* d, const void* r, int M, int N, int K,
+                    int ldd, int epi) {
+      gemm_flops += 2.0 * M * N * K;
+      return gemm_bf16_tn(a, t_max, wt, d, r, M, N, K, ldd, epi, 0, stream);
+    };
+    SB_K(SB200_KC_EMBED, embed_gather(tok_ids, w.embed, x, T, c.d_model, stream));
     for (int l = 0; l < c.n_layers; ++l) {
-      if (rmsnorm(x, ln1[l], h, T, c.d_model, c.rms_eps, stream)) return -1;
-      if (gemm_bf16_tn(h, t_max, wqkv[l], qkv, nullptr, T, qkv_dim, c.d_model, qkv_dim,
-                       EPI_STORE_BF16, 0, stream))
-        return -1;
-      if (rope_kv_write(qkv, qn[l], kn[l], w.rope_cos, w.rope_sin, tok_slot, tok_pos, page_table,
-                        max_pages, kv_layer(l), T, c.n_q_heads, c.n_kv_heads, c.rms_eps, stream))
-        return -1;
+      SB_K(SB200_KC_NORM, rmsnorm(x, ln1[l], h, T, c.d_model, c.rms_eps, stream));
+      SB_K(SB200_KC_GEMM, gemm(h, wqkv[l], qkv, nullptr, T, qkv_dim, c.d_model, qkv_dim,
+                               EPI_STORE_BF16));
+      SB_K(SB200_KC_ROPE,
+           rope_kv_write(qkv, qn[l], kn[l], w.rope_cos, w.rope_sin, tok_slot, tok_pos, page_table,
+                         max_pages, kv_layer(l), T, c.n_q_heads, c.n_kv_heads, c.rms_eps, stream));
       if (prefill) {
-        if (attn_prefill(qkv, attn, kv_layer(l), page_table, max_pages, d_work, n_work, d_seq_slot,
-                         d_seq_q_start, d_seq_q_len, d_seq_past, c.n_q_heads, c.n_kv_heads, scale,
-                         stream))
-          return -1;
+        SB_K(SB200_KC_ATTN_PREFILL,
+             attn_prefill(qkv, attn, kv_layer(l), page_table, max_pages, d_work, n_work,
+                          d_seq_slot, d_seq_q_start, d_seq_q_len, d_seq_past, c.n_q_heads,
+                          c.n_kv_heads, scale, stream));
       } else {
-        if (attn_decode(qkv, attn, kv_layer(l), page_table, max_pages, row_slot, ctx_len, T,
-                        c.n_q_heads, c.n_kv_heads, scale, stream))
-          return -1;
+        SB_K(SB200_KC_ATTN_DECODE,
+             attn_decode(qkv, attn, kv_layer(l), page_table, max_pages, row_slot, ctx_len, T,
+                         c.n_q_heads, c.n_kv_heads, scale, stream));
       }
-      if (gemm_bf16_tn(attn, t_max, wo[l], x, x, T, c.d_model, q_dim, c.d_model,
-                       EPI_RESIDUAL_BF16, 0, stream))
-        return -1;
-      if (rmsnorm(x, ln2[l], h, T, c.d_model, c.rms_eps, stream)) return -1;
-      if (gemm_bf16_tn(h, t_max, wgu[l], act, nullptr, T, 2 * c.d_ff, c.d_model, c.d_ff,
-                       EPI_SWIGLU_BF16, 0, stream))
-        return -1;
-      if (gemm_bf16_tn(act, t_max, wd[l], x, x, T, c.d_model, c.d_ff, c.d_model,
-                       EPI_RESIDUAL_BF16, 0, stream))
-        return -1;
+      SB_K(SB200_KC_GEMM, gemm(attn, wo[l], x, x, T, c.d_model, q_dim, c.d_model,
+                               EPI_RESIDUAL_BF16));
+      SB_K(SB200_KC_NORM, rmsnorm(x, ln2[l], h, T, c.d_model, c.rms_eps, stream));
+      SB_K(SB200_KC_GEMM, gemm(h, wgu[l], act, nullptr, T, 2 * c.d_ff, c.d_model, c.d_ff,
+                               EPI_SWIGLU_BF16));
+      SB_K(SB200_KC_GEMM, gemm(act, wd[l], x, x, T, c.d_model, c.d_ff, c.d_model,
+                               EPI_RESIDUAL_BF16));
     }
     (void)n_seq;
     return 0;
@@ -236,16 +295,17 @@ struct Engine {
     const auto& c = cfg;
     const bf16* src = x;
     if (idx) {
-      if (gather_rows(idx, x, hl, n, c.d_model, stream)) return -1;
+      SB_K(SB200_KC_EMBED, gather_rows(idx, x, hl, n, c.d_model, stream));
       src = hl;
     }
-    if (rmsnorm(src, w.final_norm, hn, n, c.d_model, c.rms_eps, stream)) return -1;
+    SB_K(SB200_KC_NORM, rmsnorm(src, w.final_norm, hn, n, c.d_model, c.rms_eps, stream));
     for (int r0 = 0; r0 < n; r0 += logit_rows) {
       const int nr = std::min(logit_rows, n - r0);
-      if (gemm_bf16_tn(hn + static_cast<size_t>(r0) * c.d_model, c.max_slots - r0, w.lm_head,
-                       logits, nullptr,
-                       nr, c.vocab, c.d_model, c.vocab, EPI_STORE_F32, 0, stream))
-        return -1;
+      gemm_flops += 2.0 * nr * c.vocab * c.d_model;
+      SB_K(SB200_KC_GEMM,
+           gemm_bf16_tn(hn + static_cast<size_t>(r0) * c.d_model, c.max_slots - r0, w.lm_head,
+                        logits, nullptr, nr, c.vocab, c.d_model, c.vocab, EPI_STORE_F32, 0,
+                        stream));
       SampleArgs a{};
       a.logits = logits;
       a.ldl = c.vocab;
@@ -271,7 +331,7 @@ struct Engine {
       a.tok_off = d_tok_off;
       a.eos_id = c.eos_id;
       a.ignore_eos = job.ignore_eos;
-      if (sample_greedy(a, stream)) return -1;
+      SB_K(SB200_KC_SAMPLE, sample_greedy(a, stream));
     }
     return 0;
   }
@@ -312,6 +372,10 @@ struct Engine {
 int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
   const auto& c = cfg;
   const int64_t N = job.n_rows;
+  SB_CUDA_CHECK(cudaSetDevice(device));
+  prof.reset(job.profile != 0, stream);
+  gemm_flops = 0;
+  attn_decode_bytes = 0;
   const bool embed_mode = c.embedding_model != 0;
   const bool has_fsm = !embed_mode && job.fsm_states > 0;
   const int max_new = embed_mode ? 0 : job.max_new_tokens;
@@ -393,6 +457,7 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
   for (int s = S - 1; s >= 0; --s) free_slots.push_back(s);
   std::vector<int32_t> active;  // slots in the decode batch
   std::vector<uint8_t> slot_live(S, 0);
+  std::vector<int32_t> slot_ctx(S, 0);  // host mirror: position of the next fed token
 
   auto release_all = [&]() {
     for (auto& v : slot_pages) {
@@ -418,6 +483,7 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
       }
     }
     SB_CUDA_CHECK(cudaMemcpyAsync(d_stage, h_stage, stage_cap * 4, cudaMemcpyHostToDevice, stream));
+    prof.launches[SB200_KC_OTHER] += 2;
     init_slots_kernel<<<n, 128, 0, stream>>>(d_seqs, d_pt, max_pages, page_table, slot_state,
                                              slot_ngen, slot_pos, slot_done, slot_row, slot_maxnew,
                                              slot_next_tok);
@@ -516,6 +582,7 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
       h_seqs[n] = SeqInit{slot, static_cast<int32_t>(r), T, q_len, past, n_row_tok[r], max_new,
                           has_fsm ? job.fsm_start : -1};
       slot_live[slot] = 1;
+      slot_ctx[slot] = P;
       T += q_len;
       in_tokens += P;
       ++n;
@@ -594,15 +661,23 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
     const int B = static_cast<int>(active.size());
     std::copy(active.begin(), active.end(), h_misc);
     SB_CUDA_CHECK(cudaMemcpyAsync(row_slot, h_misc, B * 4ull, cudaMemcpyHostToDevice, stream));
-    if (prepare_decode(row_slot, slot_next_tok, slot_pos, tok_ids, tok_pos, tok_slot, ctx_len, B,
-                       stream) ||
-        forward(B, false, B, nullptr, 0, nullptr, nullptr, nullptr, nullptr) ||
+    prof.begin(SB200_KC_OTHER);
+    const int prc = prepare_decode(row_slot, slot_next_tok, slot_pos, tok_ids, tok_pos, tok_slot,
+                                   ctx_len, B, stream);
+    prof.end();
+    if (prc || forward(B, false, B, nullptr, 0, nullptr, nullptr, nullptr, nullptr) ||
         head_and_sample(B, nullptr, row_slot, job, has_fsm)) {
       rc = -1;
       break;
     }
     decode_tokens += B;
     ++steps_decode;
+    {
+      int64_t ctx_sum = 0;
+      for (int s : active) ctx_sum += ++slot_ctx[s];
+      attn_decode_bytes += static_cast<double>(ctx_sum) * c.n_layers * c.n_kv_heads * 2.0 *
+                           kHeadDim * 2.0;
+    }
     if (retire()) {
       rc = -1;
       break;
@@ -612,7 +687,14 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
   }
   cudaStreamSynchronize(stream);
   release_all();
+  prof.resolve();
   if (stats) {
+    for (int i = 0; i < SB200_KC_COUNT; ++i) {
+      stats->kernel_ms[i] = prof.ms[i];
+      stats->kernel_launches[i] = prof.launches[i];
+    }
+    stats->gemm_flops = gemm_flops;
+    stats->attn_decode_bytes = attn_decode_bytes;
     stats->rows_done = rows_done;
     stats->input_tokens = in_tokens;
     stats->prefill_tokens = prefill_tokens;
@@ -691,6 +773,7 @@ void sb200_engine_destroy(void* engine) { delete static_cast<Engine*>(engine); }
 
 int sb200_engine_set_vocab(void* engine, const uint8_t* tok_bytes, const int32_t* tok_off) {
   auto* e = static_cast<Engine*>(engine);
+  SB_CUDA_CHECK(cudaSetDevice(e->device));
   const int V = e->cfg.vocab;
   cudaFree(e->d_tok_bytes);
   cudaFree(e->d_tok_off);

@@ -57,13 +57,19 @@ class JobC(C.Structure):
                 ("fsm_states", C.c_int), ("fsm_start", C.c_int),
                 ("out_tokens_dev", C.c_void_p), ("out_len_dev", C.c_void_p),
                 ("out_embed_dev", C.c_void_p),
-                ("progress", PROGRESS_FN), ("progress_user", C.c_void_p)]
+                ("progress", PROGRESS_FN), ("progress_user", C.c_void_p), ("profile", C.c_int)]
+
+
+KERNEL_CLASSES = ["gemm", "attn_decode", "attn_prefill", "norm", "rope", "sample", "embed",
+                  "other"]
+_STAT_INTS = ("rows_done", "input_tokens", "prefill_tokens", "decode_tokens", "prefill_steps",
+              "decode_steps", "rows_truncated", "prefix_cached_tokens")
 
 
 class JobStatsC(C.Structure):
-    _fields_ = [(n, C.c_int64) for n in ("rows_done", "input_tokens", "prefill_tokens",
-                                         "decode_tokens", "prefill_steps", "decode_steps",
-                                         "rows_truncated", "prefix_cached_tokens")]
+    _fields_ = [(n, C.c_int64) for n in _STAT_INTS] + \
+               [("kernel_launches", C.c_int64 * 8), ("kernel_ms", C.c_double * 8),
+                ("gemm_flops", C.c_double), ("attn_decode_bytes", C.c_double)]
 
 
 L.register("sb200_engine_create", C.c_int, [C.POINTER(EngineConfigC), C.POINTER(EngineWeightsC),
@@ -313,7 +319,8 @@ class LocalEngine:
                  ignore_eos: bool = False, truncate_rows: bool = True, share_prefix: bool = True,
                  fsm_limits: Optional[FsmLimits] = None,
                  progress: Optional[Callable[[int, int, int], None]] = None,
-                 return_tokens: bool = False, return_text: bool = True) -> GenerationResult:
+                 return_tokens: bool = False, return_text: bool = True,
+                 profile: bool = False) -> GenerationResult:
         dev = self.device
         t0 = time.perf_counter()
         data, off = rows_to_blob(rows)
@@ -349,6 +356,7 @@ class LocalEngine:
             job.out_len_dev = L.ptr(d_len)
             job.out_embed_dev = L.ptr(d_emb)
             job.progress = cb
+            job.profile = int(profile)
             st = JobStatsC()
             torch.cuda.synchronize(dev)
             L.check(L.lib().sb200_engine_run(self._h, C.byref(job), C.byref(st)))
@@ -371,7 +379,10 @@ class LocalEngine:
                     fl, oo = flat.cpu().numpy(), ooff.cpu().numpy()
                     out_tokens = [fl[oo[i]:oo[i + 1]].tolist() for i in range(n_rows)]
             t_end = time.perf_counter()
-        stats = {k: int(getattr(st, k)) for k, _ in JobStatsC._fields_}
+        stats = {k: int(getattr(st, k)) for k in _STAT_INTS}
+        stats["kernel_launches"] = dict(zip(KERNEL_CLASSES, list(st.kernel_launches)))
+        stats["kernel_ms"] = dict(zip(KERNEL_CLASSES, list(st.kernel_ms)))
+        stats["gemm_flops"], stats["attn_decode_bytes"] = st.gemm_flops, st.attn_decode_bytes
         stats.update(output_tokens=n_out, n_rows=n_rows, h2d_bytes=int(data.nbytes + off.nbytes),
                      t_host_prep_s=t_host - t0, t_tokenize_s=t_tok - t_host,
                      t_engine_s=t_run - t_tok, t_detok_s=t_end - t_run, t_total_s=t_end - t0,

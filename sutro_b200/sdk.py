@@ -1,0 +1,322 @@
+"""`Sutro` — the local, B200-native counterpart of the reference SDK client for the
+infer() hot path (reference: sutro/sdk.py:46, `class Sutro`).
+
+Drop-in surface (same names, positional order, defaults, return and error
+conventions as the reference):
+  infer()                 sutro/sdk.py:434-502   -> job-id str | None
+  infer_per_model()       sutro/sdk.py:655-757   -> list[str]
+  await_job_completion()  sutro/sdk.py:1493-1568 -> DataFrame | None
+  get_job_results()       sutro/sdk.py:1037-1190 -> DataFrame (JSON top-level unpack)
+  get_job_status() / fetch_job() / list_jobs() / cancel_job()
+What changes is what happens at the reference's single process boundary
+(`do_request("POST", "batch-inference")`, sutro/sdk.py:223): instead of shipping the
+column to a hosted service, the rows go through `engine.LocalEngine.generate` on this
+machine's B200(s).  Jobs complete before infer() returns, so the polling helpers
+resolve immediately; results are kept in memory and (like the reference,
+sutro/sdk.py:1065-1117) cached as snappy parquet under ~/.sutro/job-results/.
+
+Conventions kept from the reference: bad arguments raise ValueError; engine/service
+failures print a message and return None; pandas input is updated in place with
+`output_column`, other frames are left untouched; outputs are positional.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+import uuid
+from typing import Any, Dict, List, Optional, Type, Union
+
+import pandas as pd
+
+from .common import (ModelOptions, handle_data_helper, is_frame, normalize_output_schema, pl,
+                     to_colored_text)
+from .interfaces import BaseSutroClient, JobStatus
+
+JOB_NAME_CHAR_LIMIT = 45          # sutro/sdk.py:39-40
+JOB_DESCRIPTION_CHAR_LIMIT = 512
+
+
+class _Job:
+    def __init__(self, job_id, model, n_rows, name, description, priority):
+        self.job_id, self.model, self.n_rows = job_id, model, n_rows
+        self.name, self.description, self.priority = name, description, priority
+        self.status = JobStatus.QUEUED
+        self.inputs: Optional[List[str]] = None
+        self.outputs: Optional[list] = None
+        self.embeddings = None
+        self.stats: Dict[str, Any] = {}
+        self.failure_reason: Optional[str] = None
+        self.created = time.time()
+        self.cost_estimate: Optional[float] = None
+
+
+class Sutro(BaseSutroClient):
+    def __init__(self, devices: Optional[List[int]] = None, weights_seed: int = 0,
+                 engine_options: Optional[Dict[str, Any]] = None, cache_dir: Optional[str] = None,
+                 verbose: bool = True):
+        self.devices = devices or [0]
+        self.weights_seed = weights_seed
+        self.engine_options = dict(engine_options or {})
+        self.cache_dir = os.path.expanduser(cache_dir or "~/.sutro/job-results")
+        self.verbose = verbose
+        self._engines: Dict[str, Any] = {}
+        self._jobs: Dict[str, _Job] = {}
+
+    # ------------------------------------------------------------------ engines
+    def _say(self, msg: str, state: str = None):
+        if self.verbose:
+            print(to_colored_text(msg, state))
+
+    def _engine(self, model: str):
+        if model not in self._engines:
+            from .engine import LocalEngine
+            self._say(f"Loading {model} on cuda:{self.devices[0]} (random-init weights, seed "
+                      f"{self.weights_seed}: no checkpoints are available offline)")
+            self._engines[model] = LocalEngine.from_seed(model, seed=self.weights_seed,
+                                                         device=self.devices[0],
+                                                         **self.engine_options)
+        return self._engines[model]
+
+    def register_engine(self, model: str, engine) -> None:
+        """Use a pre-built LocalEngine (tests, benchmarks, multi-GPU workers)."""
+        self._engines[model] = engine
+
+    # ------------------------------------------------------------------ the hot path
+    def _run_one_batch_inference(self, data, model, column, output_column, job_priority,
+                                 json_schema, sampling_params, system_prompt, cost_estimate,
+                                 stay_attached, random_seed_per_input, truncate_rows, name,
+                                 description):
+        if name is not None and len(name) > JOB_NAME_CHAR_LIMIT:
+            raise ValueError(f"Job name cannot exceed {JOB_NAME_CHAR_LIMIT} characters.")
+        if description is not None and len(description) > JOB_DESCRIPTION_CHAR_LIMIT:
+            raise ValueError(
+                f"Job description cannot exceed {JOB_DESCRIPTION_CHAR_LIMIT} characters.")
+        input_data = handle_data_helper(data, column)
+        sp = dict(sampling_params or {})
+        temperature = sp.get("temperature", 0) or 0
+        if temperature != 0 or sp.get("top_p", 1) not in (1, 1.0, None) or \
+                sp.get("top_k", -1) not in (-1, 0, None):
+            raise ValueError("the local engine decodes greedily; sampling_params may only set "
+                             "max_tokens / max_new_tokens / ignore_eos (temperature 0)")
+        if random_seed_per_input:
+            self._say("random_seed_per_input has no effect under greedy decoding")
+        max_new = int(sp.get("max_tokens", sp.get("max_new_tokens", 64)))
+
+        job = _Job("job-" + uuid.uuid4().hex[:24], model, len(input_data), name, description,
+                   job_priority)
+        self._jobs[job.job_id] = job
+        name_text = f" and name {name}" if name is not None else ""
+        self._say(f"🛠 Priority {job_priority} Job created with ID: {job.job_id}{name_text}",
+                  "success")
+        self._say(f"Model: {model}")
+        try:
+            eng = self._engine(model)
+            job.status = JobStatus.RUNNING
+            if cost_estimate:
+                # dry run: count input tokens only (the reference asks the service for a
+                # dollar estimate; locally the marginal cost is zero)
+                toks = eng.tokenizer.encode([("" if x is None else str(x)) for x in input_data])
+                job.stats = {"input_tokens": sum(map(len, toks))}
+                job.cost_estimate = 0.0
+                job.status = JobStatus.SUCCEEDED
+                self._say(f"✔ Cost estimates retrieved for job {job.job_id}: $0.0 "
+                          f"({job.stats['input_tokens']} input tokens)", "success")
+                return job.job_id
+            t0 = time.perf_counter()
+            res = eng.generate(input_data, system_prompt=system_prompt, json_schema=json_schema,
+                               max_new_tokens=max_new, ignore_eos=bool(sp.get("ignore_eos", False)),
+                               truncate_rows=truncate_rows)
+            dt = time.perf_counter() - t0
+        except KeyboardInterrupt:
+            job.status = JobStatus.CANCELLED
+            return None
+        except ValueError:
+            job.status = JobStatus.FAILED
+            raise
+        except Exception as e:  # engine failure: print + None, like a non-200 (sdk.py:225-234)
+            job.status, job.failure_reason = JobStatus.FAILED, str(e)
+            self._say(f"Error: {e}", "fail")
+            return None
+        job.inputs = input_data
+        job.stats = res.stats
+        if res.embeddings is not None:
+            job.embeddings = res.embeddings
+            job.outputs = [row.tolist() for row in res.embeddings]
+        else:
+            job.outputs = res.outputs
+        job.status = JobStatus.SUCCEEDED
+        tps = (res.stats.get("input_tokens", 0) + res.stats.get("output_tokens", 0)) / max(dt, 1e-9)
+        self._say(f"Input tokens processed: {res.stats.get('input_tokens', 0)}, Output tokens "
+                  f"generated: {res.stats.get('output_tokens', 0)}, Total tokens/s: {tps:.0f}")
+        if not stay_attached:
+            self._say(f"Use `so.get_job_status('{job.job_id}')` to check the status of the job")
+            return job.job_id
+        # attached: preview + positional write-back (sdk.py:406-430)
+        results = job.outputs
+        if is_frame(data):
+            if isinstance(data, pd.DataFrame):
+                data[output_column] = results
+                preview = data
+            elif pl is not None and isinstance(data, pl.DataFrame):
+                preview = data.with_columns(pl.Series(output_column, results))
+            else:
+                preview = data.append_column(output_column, [results])
+            if self.verbose:
+                print(preview)
+            self._say("✔ Displaying result preview. You can join the results on the original "
+                      f"dataframe with `so.get_job_results('{job.job_id}', "
+                      "with_original_df=<original_df>)`", "success")
+        else:
+            if self.verbose:
+                print(results if len(results) <= 20 else results[:20] + ["..."])
+            self._say("✔ Job results received. You can re-obtain the results with "
+                      f"`so.get_job_results('{job.job_id}')`", "success")
+        return job.job_id
+
+    def infer(
+        self,
+        data,
+        model: ModelOptions = "gemma-3-12b-it",
+        name: Optional[str] = None,
+        description: Optional[str] = None,
+        column: Union[str, List[str]] = None,
+        output_column: str = "inference_result",
+        job_priority: int = 0,
+        output_schema: Union[Dict[str, Any], Type[Any]] = None,
+        sampling_params: dict = None,
+        system_prompt: str = None,
+        dry_run: bool = False,
+        stay_attached: Optional[bool] = None,
+        random_seed_per_input: bool = False,
+        truncate_rows: bool = True,
+    ):
+        """Run inference over `data` on the local B200 engine; returns the job id."""
+        if stay_attached is None:
+            stay_attached = job_priority == 0
+        json_schema = None
+        if output_schema:
+            json_schema = normalize_output_schema(output_schema)
+        return self._run_one_batch_inference(data, model, column, output_column, job_priority,
+                                             json_schema, sampling_params, system_prompt, dry_run,
+                                             stay_attached, random_seed_per_input, truncate_rows,
+                                             name, description)
+
+    def infer_per_model(self, data, models: List[ModelOptions], names: List[str] = None,
+                        descriptions: List[str] = None, column=None,
+                        output_column: str = "inference_result", job_priority: int = 0,
+                        output_schema=None, sampling_params: dict = None, system_prompt: str = None,
+                        dry_run: bool = False, random_seed_per_input: bool = False,
+                        truncate_rows: bool = True) -> List[str]:
+        """One detached job per model (reference: sutro/sdk.py:655-757)."""
+        names = names if isinstance(names, list) else [None] * len(models)
+        descriptions = descriptions if isinstance(descriptions, list) else [None] * len(models)
+        if len(names) != len(models) or len(descriptions) != len(models):
+            raise ValueError("names/descriptions must match the number of models")
+        return [self.infer(data, m, names[i], descriptions[i], column, output_column, job_priority,
+                           output_schema, sampling_params, system_prompt, dry_run, False,
+                           random_seed_per_input, truncate_rows) for i, m in enumerate(models)]
+
+    # ------------------------------------------------------------------ job surface
+    def _job(self, job_id: str) -> _Job:
+        if job_id not in self._jobs:
+            raise ValueError(f"Unknown job id {job_id}")
+        return self._jobs[job_id]
+
+    def get_job_status(self, job_id: str) -> JobStatus:
+        return self._job(job_id).status
+
+    def fetch_job(self, job_id: str) -> Dict[str, Any]:
+        j = self._job(job_id)
+        return {"job_id": j.job_id, "status": j.status.value, "model": j.model, "name": j.name,
+                "description": j.description, "num_rows": j.n_rows, "job_priority": j.priority,
+                "input_tokens": j.stats.get("input_tokens"),
+                "output_tokens": j.stats.get("output_tokens"), "failure_reason": j.failure_reason,
+                "cost_estimate": j.cost_estimate, "datetime_created": j.created}
+
+    def list_jobs(self) -> List[Dict[str, Any]]:
+        return [self.fetch_job(j) for j in self._jobs]
+
+    def cancel_job(self, job_id: str):
+        j = self._job(job_id)
+        if not j.status.is_terminal():
+            j.status = JobStatus.CANCELLED
+        return {"job_id": job_id, "status": j.status.value}
+
+    def await_job_completion(self, job_id: str, timeout: Optional[int] = 7200,
+                             obtain_results: bool = True, output_column: str = "inference_result",
+                             is_cost_estimate: bool = False):
+        """Local jobs are already terminal when infer() returns; this resolves the job id
+        to its results frame exactly like the reference (sutro/sdk.py:1493-1568)."""
+        status = self.get_job_status(job_id)
+        if status == JobStatus.SUCCEEDED:
+            self._say("Job completed! Retrieving results..." if obtain_results
+                      else "Job completed!", "success")
+            if obtain_results and not is_cost_estimate:
+                return self.get_job_results(job_id, output_column=output_column)
+            return None
+        if status == JobStatus.FAILED:
+            self._say("Job has failed", "fail")
+        elif status == JobStatus.CANCELLED:
+            self._say("Job has been cancelled")
+        return None
+
+    def get_job_results(self, job_id: str, include_inputs: bool = False,
+                        include_cumulative_logprobs: bool = False, with_original_df=None,
+                        output_column: str = "inference_result", disable_cache: bool = False,
+                        unpack_json: bool = True):
+        """Results frame with the reference's column contract (sutro/sdk.py:1037-1190):
+        [inputs] / <output_column>, JSON outputs fanned out to top-level keys when the
+        first row parses as a JSON object.  Returns a pandas DataFrame (polars when the
+        original frame is polars and polars is installed)."""
+        j = self._job(job_id)
+        if j.status != JobStatus.SUCCEEDED or j.outputs is None:
+            self._say(f"Job {job_id} has no results (status {j.status.value})", "fail")
+            return None
+        if include_cumulative_logprobs:
+            raise ValueError("cumulative logprobs are not produced by the local greedy engine")
+        path = os.path.join(self.cache_dir, f"{job_id}.snappy.parquet")
+        cols: Dict[str, Any] = {}
+        if include_inputs:
+            cols["inputs"] = j.inputs
+        cols[output_column] = j.outputs
+        df = pd.DataFrame(cols)
+        if not disable_cache:
+            try:
+                os.makedirs(self.cache_dir, exist_ok=True)
+                df.to_parquet(path, compression="snappy")
+            except Exception as e:  # cache is best effort
+                self._say(f"(results cache not written: {e})")
+        if unpack_json and len(df) and isinstance(df[output_column].iloc[0], str):
+            try:
+                first = json.loads(df[output_column].iloc[0])
+                if isinstance(first, dict):
+                    decoded = [json.loads(s) for s in df[output_column]]
+                    for key in first.keys():
+                        df[key] = [d.get(key) if isinstance(d, dict) else None for d in decoded]
+                    if sorted(first.keys()) == ["content", "reasoning_content"] and \
+                            isinstance(first["content"], dict):
+                        for key in first["content"].keys():
+                            df[key] = [d["content"].get(key) for d in decoded]
+                        df = df.drop(columns=["content"])
+                    df = df.drop(columns=[output_column])
+            except Exception:
+                pass  # first row is not JSON: leave the column as text (sdk.py:1168-1170)
+        if with_original_df is not None:
+            if isinstance(with_original_df, pd.DataFrame):
+                out = with_original_df.copy()
+                for c in df.columns:
+                    out[c] = df[c].values
+                return out
+            if pl is not None and isinstance(with_original_df, pl.DataFrame):
+                return with_original_df.with_columns(pl.from_pandas(df))
+        return df
+
+    def get_job_embeddings(self, job_id: str):
+        """fp32 [n_rows, d] array for embedding-model jobs (zero-copy alternative to the
+        list-of-lists results column)."""
+        return self._job(job_id).embeddings
+
+    # quotas / datasets / auth are properties of the hosted service, not of this path
+    def try_authentication(self, api_key: str = None):
+        return {"authenticated": True, "backend": "local-b200"}

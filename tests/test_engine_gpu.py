@@ -3,9 +3,12 @@ architectures: tokenizer ids bit-exact, greedy token ids equal wherever the orac
 top-1 margin is not a near-tie, constrained outputs valid and equal, embeddings close.
 
 Tolerances (stated once, used below):
-  MARGIN_EPS   greedy decisions are compared while the oracle's top-1/top-2 logit gap
-               exceeds 0.02 (logit std is ~1); after the first closer call the two
-               sequences may legitimately diverge (bf16 accumulation order).
+  MARGIN_EPS   a greedy decision must equal the oracle's whenever the oracle's top-1/top-2
+               logit gap exceeds 0.06 (logit std is ~1; two bf16 pipelines that differ only
+               in fp32 summation order disagree by ~0.02 on these tiny models).  Below that
+               gap the engine may pick the oracle's runner-up instead (a near-tie flip);
+               anything else fails.  After a flip the sequences legitimately diverge, so
+               the comparison stops there.
   EMB_TOL      embedding vectors: max abs diff 2e-2 on unit-norm vectors.
 """
 import json
@@ -25,7 +28,7 @@ from sutro_b200.schema_fsm import FsmLimits, compile_schema
 
 pytestmark = pytest.mark.gpu
 
-MARGIN_EPS = 0.02
+MARGIN_EPS = 0.06
 EMB_TOL = 2e-2
 SYS = synth.README_SYSTEM_PROMPT
 
@@ -49,16 +52,17 @@ def build(name, seed=0, **kw):
     return spec, w, v, eng
 
 
-def compare_greedy(got: List[int], ref, label=""):
-    """Equal up to the first oracle decision whose margin is below MARGIN_EPS."""
-    n_cmp = len(ref.margins)
-    for i, m in enumerate(ref.margins):
-        if m < MARGIN_EPS:
-            n_cmp = i
-            break
-    want = ref.tokens[:n_cmp]
-    assert got[:len(want)] == want, (label, got, ref.tokens, ref.margins)
-    return n_cmp, len(ref.margins)
+def compare_greedy(got: List[int], ref, label="", eos_id=-1):
+    """Returns (#decisions verified equal, #decisions the oracle made, #near-tie flips)."""
+    toks = list(ref.tokens) + ([eos_id] if len(ref.margins) > len(ref.tokens) else [])
+    for i, want in enumerate(toks):
+        have = got[i] if i < len(got) else eos_id          # the engine stopped: it chose EOS
+        if have == want:
+            continue
+        assert ref.margins[i] < MARGIN_EPS, (label, i, got, ref.tokens, ref.margins)
+        assert have == ref.runner_up[i], (label, i, have, ref.runner_up[i])
+        return i, len(toks), 1
+    return len(toks), len(toks), 0
 
 
 ROWS = synth.README_REVIEWS + synth.product_reviews(9, seed=7) + ["", "x", "ok ok ok"]
@@ -92,15 +96,15 @@ def test_unconstrained_greedy_matches_oracle(name):
                        return_tokens=True)
     ref_tok, model = RefTokenizer(v), RefModel(spec, w)
     tpl = VB.chat_template(spec.family, SYS)
-    compared = total = 0
+    compared = total = flips = 0
     for row, got in zip(ROWS, res.out_tokens):
         prompt = ref_tok.render(tpl, row, spec.max_position - 12)
         r = model.generate(prompt, 12, v.eos_id, ignore_eos=True)
         assert len(got) == 12
-        c, t = compare_greedy(got, r, row[:30])
-        compared += c
-        total += t
+        c, t, f = compare_greedy(got, r, row[:30], v.eos_id)
+        compared, total, flips = compared + c, total + t, flips + f
     assert compared >= 0.5 * total, (compared, total)   # the criterion is not vacuous
+    assert flips <= len(ROWS) // 3, flips
     assert res.stats["rows_done"] == len(ROWS)
     assert res.stats["prefix_cached_tokens"] >= 16       # the system prompt was shared
 
@@ -134,16 +138,16 @@ def test_schema_constrained_outputs_validate_and_match_oracle(schema_model):
     fsm = TokenFSM(dfa, v)
     ref_tok, model = RefTokenizer(v), RefModel(spec, w)
     tpl = VB.chat_template(spec.family, SYS)
-    compared = total = 0
+    compared = total = flips = 0
     for row, text, got in zip(ROWS, res.outputs, res.out_tokens):
         obj = json.loads(text)                       # every output is valid JSON ...
         schema_model.model_validate(obj)             # ... and an instance of the schema
         assert dfa.matches(text.encode("utf-8"))
         r = model.generate(ref_tok.render(tpl, row, spec.max_position - 64), 64, v.eos_id, fsm=fsm)
-        c, t = compare_greedy(got, r, row[:30])
-        compared += c
-        total += t
+        c, t, f = compare_greedy(got, r, row[:30], v.eos_id)
+        compared, total, flips = compared + c, total + t, flips + f
     assert compared >= 0.5 * total, (compared, total)
+    assert flips <= len(ROWS) // 3, flips
 
 
 def test_max_new_tokens_truncates_and_eos_stops():

@@ -1,0 +1,153 @@
+"""CPU tests of the drop-in boundary: argument handling, error conventions and result
+shaping follow the reference (sutro/common.py:72-163, sutro/sdk.py:186-193, :406-432,
+:1111-1170; reference tests/test_sdk.py:326-334).  The engine is replaced by a stub —
+these tests are about the host logic only."""
+import inspect
+import json
+
+import numpy as np
+import pandas as pd
+import pytest
+from pydantic import BaseModel
+
+import sutro_b200 as so
+from sutro_b200 import common, interfaces
+from sutro_b200.engine import GenerationResult, rows_to_blob, blob_to_rows
+from sutro_b200.sdk import Sutro
+
+
+class Sentiment(BaseModel):
+    sentiment: str
+
+
+class StubEngine:
+    def __init__(self, as_json=True):
+        self.calls, self.as_json = [], as_json
+
+    def generate(self, rows, **kw):
+        self.calls.append((list(rows), kw))
+        outs = [json.dumps({"sentiment": f"s{i}"}) if self.as_json else f"out-{i}"
+                for i in range(len(rows))]
+        return GenerationResult(outs, None, None, {"input_tokens": 10, "output_tokens": 5})
+
+
+def client(as_json=True):
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+    c.register_engine("qwen-3-4b", StubEngine(as_json))
+    return c
+
+
+def test_infer_signature_matches_reference_positional_order():
+    want = ["self", "data", "model", "name", "description", "column", "output_column",
+            "job_priority", "output_schema", "sampling_params", "system_prompt", "dry_run",
+            "stay_attached", "random_seed_per_input", "truncate_rows"]
+    assert list(inspect.signature(Sutro.infer).parameters) == want
+    assert list(inspect.signature(interfaces.BaseSutroClient.infer).parameters) == want
+    p = inspect.signature(Sutro.infer).parameters
+    assert p["model"].default == "gemma-3-12b-it" and p["output_column"].default == "inference_result"
+    assert p["job_priority"].default == 0 and p["truncate_rows"].default is True
+    assert list(inspect.signature(Sutro.await_job_completion).parameters) == [
+        "self", "job_id", "timeout", "obtain_results", "output_column", "is_cost_estimate"]
+    assert callable(so.infer) and callable(so.get_job_results)
+
+
+def test_job_status_enum_matches_reference():
+    names = ["UNKNOWN", "QUEUED", "STARTING", "RUNNING", "SUCCEEDED", "CANCELLING", "CANCELLED",
+             "FAILED"]
+    assert [s.name for s in interfaces.JobStatus] == names
+    assert interfaces.JobStatus.SUCCEEDED.is_terminal() and not interfaces.JobStatus.RUNNING.is_terminal()
+
+
+def test_missing_column_raises_value_error():           # reference tests/test_sdk.py:326-334
+    with pytest.raises(ValueError, match="Column name must be specified"):
+        client().infer(pd.DataFrame({"a": ["x"]}), model="qwen-3-4b")
+
+
+def test_name_and_description_limits():                  # sutro/sdk.py:186-193
+    with pytest.raises(ValueError, match="Job name cannot exceed 45"):
+        client().infer(["x"], model="qwen-3-4b", name="n" * 46)
+    with pytest.raises(ValueError, match="description cannot exceed 512"):
+        client().infer(["x"], model="qwen-3-4b", description="d" * 513)
+
+
+def test_invalid_schema_raises_value_error():            # sutro/common.py:161-163
+    with pytest.raises(ValueError, match="Invalid output schema type"):
+        client().infer(["x"], model="qwen-3-4b", output_schema="nope")
+    assert common.normalize_output_schema(Sentiment)["properties"]["sentiment"]["type"] == "string"
+    assert common.normalize_output_schema({"type": "object"}) == {"type": "object"}
+
+
+def test_column_concatenation_with_literal_separators():  # sutro/common.py:72-108
+    df = pd.DataFrame({"a": ["x", None], "b": [1, 2]})
+    assert common.handle_data_helper(df, ["a", ": ", "b"]) == ["x: 1", ": 2"]
+    assert common.handle_data_helper(df, "b") == [1, 2]
+    assert common.handle_data_helper(["p", "q"]) == ["p", "q"]
+    with pytest.raises(ValueError, match="Unsupported data type"):
+        common.handle_data_helper(42)
+
+
+def test_attached_pandas_is_updated_in_place_and_job_id_returned():   # sutro/sdk.py:406-430
+    c = client()
+    df = pd.DataFrame({"review": ["a", "b", "c"]})
+    job_id = c.infer(df, model="qwen-3-4b", column="review", output_schema=Sentiment,
+                     system_prompt="classify")
+    assert isinstance(job_id, str) and job_id.startswith("job-")
+    assert list(df["inference_result"]) == [json.dumps({"sentiment": f"s{i}"}) for i in range(3)]
+    eng = c._engines["qwen-3-4b"]
+    rows, kw = eng.calls[0]
+    assert rows == ["a", "b", "c"] and kw["system_prompt"] == "classify"
+    assert kw["json_schema"]["properties"]["sentiment"]["type"] == "string"
+    assert c.get_job_status(job_id) == interfaces.JobStatus.SUCCEEDED
+
+
+def test_detached_returns_job_id_and_results_are_unpacked():   # sdk.py:256-273, :1137-1154
+    c = client()
+    df = pd.DataFrame({"review": ["a", "b"]})
+    job_id = c.infer(df, model="qwen-3-4b", column="review", job_priority=1)
+    assert "inference_result" not in df.columns           # detached: no write-back
+    res = c.await_job_completion(job_id)
+    assert list(res.columns) == ["sentiment"] and list(res["sentiment"]) == ["s0", "s1"]
+    joined = c.get_job_results(job_id, with_original_df=df, include_inputs=True)
+    assert list(joined.columns) == ["review", "inputs", "sentiment"]
+    raw = c.get_job_results(job_id, unpack_json=False, output_column="out")
+    assert list(raw.columns) == ["out"]
+
+
+def test_plain_text_outputs_are_not_unpacked():
+    c = client(as_json=False)
+    job_id = c.infer(["a", "b"], model="qwen-3-4b", stay_attached=False)
+    res = c.get_job_results(job_id)
+    assert list(res.columns) == ["inference_result"] and list(res["inference_result"]) == ["out-0", "out-1"]
+
+
+def test_engine_failure_prints_and_returns_none():        # non-200 convention, sdk.py:225-234
+    c = Sutro(verbose=False)
+
+    class Boom:
+        def generate(self, rows, **kw):
+            raise RuntimeError("device lost")
+    c.register_engine("qwen-3-4b", Boom())
+    assert c.infer(["x"], model="qwen-3-4b") is None
+    assert c.list_jobs()[0]["status"] == "FAILED"
+
+
+def test_non_greedy_sampling_is_rejected():
+    with pytest.raises(ValueError, match="greedily"):
+        client().infer(["x"], model="qwen-3-4b", sampling_params={"temperature": 0.7})
+
+
+def test_infer_per_model_returns_list_of_ids():           # sutro/sdk.py:750-757
+    c = client()
+    c.register_engine("m2", StubEngine())
+    ids = c.infer_per_model(["x"], ["qwen-3-4b", "m2"])
+    assert len(ids) == 2 and all(i.startswith("job-") for i in ids)
+
+
+def test_rows_to_blob_roundtrip_arrow_style():
+    rows = ["héllo", "", None, "x" * 1000, "日本"]
+    data, off = rows_to_blob(rows)
+    assert off.dtype == np.int64 and len(off) == 6 and off[0] == 0
+    assert blob_to_rows(data, off) == ["héllo", "", "", "x" * 1000, "日本"]
+    import pyarrow as pa
+    d2, o2 = rows_to_blob(pa.array(["a", "bc"]).slice(1))
+    assert blob_to_rows(d2, o2) == ["bc"]
