@@ -166,6 +166,8 @@ typedef struct {
   sb200_progress_fn progress;     /* may be NULL                                        */
   void* progress_user;
   int profile;                    /* 1: time every kernel launch with CUDA events        */
+  float* out_first_logits_dev;    /* optional [n_rows, vocab]: fp32 logits of each row's first
+                                     decision (teacher-forced parity checks); NULL = off   */
 } sb200_job;
 
 /* kernel classes for the per-class launch counts / device times in sb200_job_stats */

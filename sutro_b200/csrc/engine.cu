@@ -139,6 +139,16 @@ struct Profiler {
     if (_rc) return -1;        \
   } while (0)
 
+__global__ void scatter_logits_kernel(const float* __restrict__ logits,
+                                      const int32_t* __restrict__ row_slot,
+                                      const int32_t* __restrict__ slot_row, float* __restrict__ dst,
+                                      int vocab) {
+  const int row = slot_row[row_slot[blockIdx.x]];
+  const float4* src = reinterpret_cast<const float4*>(logits + static_cast<size_t>(blockIdx.x) * vocab);
+  float4* d = reinterpret_cast<float4*>(dst + static_cast<size_t>(row) * vocab);
+  for (int i = threadIdx.x; i < vocab / 4; i += blockDim.x) d[i] = src[i];
+}
+
 template <typename T>
 int dmalloc(T** p, size_t n) {
   SB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
@@ -291,7 +301,7 @@ struct Engine {
   // final norm + lm_head + masked greedy sampling for `n` rows whose hidden
   // states are rows idx[0..n) of x (idx == nullptr: rows 0..n).
   int head_and_sample(int n, const int32_t* idx, const int32_t* d_row_slot,
-                      const sb200_job& job, bool has_fsm) {
+                      const sb200_job& job, bool has_fsm, bool first_decision = false) {
     const auto& c = cfg;
     const bf16* src = x;
     if (idx) {
@@ -306,6 +316,11 @@ struct Engine {
            gemm_bf16_tn(hn + static_cast<size_t>(r0) * c.d_model, c.max_slots - r0, w.lm_head,
                         logits, nullptr, nr, c.vocab, c.d_model, c.vocab, EPI_STORE_F32, 0,
                         stream));
+      if (first_decision && job.out_first_logits_dev) {
+        scatter_logits_kernel<<<nr, 256, 0, stream>>>(logits, d_row_slot + r0, slot_row,
+                                                      job.out_first_logits_dev, c.vocab);
+        SB_CUDA_CHECK(cudaGetLastError());
+      }
       SampleArgs a{};
       a.logits = logits;
       a.ldl = c.vocab;
@@ -503,7 +518,7 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
       SB_CUDA_CHECK(cudaGetLastError());
       return 0;
     }
-    return head_and_sample(n, last_idx, d_misc /* seq_slot */, job, has_fsm);
+    return head_and_sample(n, last_idx, d_misc /* seq_slot */, job, has_fsm, true);
   };
 
   // ---- shared prefix: compute its KV once, every row's page table points at it ----

