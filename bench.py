@@ -91,6 +91,15 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in self.rows if len(r) >= 7)}
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg: str):
+    """progress to stderr (stdout carries exactly one JSON line)"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench +{time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def make_rows(n: int, seed: int):
     from sutro_b200 import synth
     return synth.product_reviews(n, seed=seed)
@@ -185,6 +194,9 @@ def main():
     ap.add_argument("--max-prefill-tokens", type=int, default=16384)
     ap.add_argument("--cpu-rows", type=int, default=8, help="rows in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kv-pages", type=int, default=None,
+                    help="KV pool size in pages (default: 80%% of free memory); small pools keep "
+                         "ncu's save/restore cheap")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -219,8 +231,9 @@ def main():
         bcast_ms = (time.perf_counter() - tb) * 1e3
     vocab = VB.build_vocab(spec.family, spec.vocab_size, seed=0)
     eng = LocalEngine(spec, weights, vocab, device=dev, max_slots=args.max_slots,
-                      max_prefill_tokens=args.max_prefill_tokens)
+                      max_prefill_tokens=args.max_prefill_tokens, kv_pages=args.kv_pages)
     setup_s = time.perf_counter() - t0
+    log(f"engine ready in {setup_s:.1f}s (kv_pages={eng.kv_pages})")
 
     def fence():
         torch.cuda.synchronize()
@@ -236,15 +249,22 @@ def main():
         return eng.generate(rows, system_prompt=SYSTEM_PROMPT, json_schema=SCHEMA,
                             max_new_tokens=MAX_NEW, profile=profile)
 
+    log(f"{len(shards)} shards of {args.rows} rows generated")
     for i in range(args.warmup):
-        run(shards[i])
+        r = run(shards[i])
+        log(f"warmup {i}: {r.stats['t_total_s']:.2f}s "
+            f"({args.rows / r.stats['t_total_s']:.0f} rows/s, engine {r.stats['t_engine_s']:.2f}s, "
+            f"prefill_steps {r.stats['prefill_steps']}, decode_steps {r.stats['decode_steps']})")
     clocks = ClockSampler(local)
     fence()
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t_start = time.perf_counter()
-    results = [run(shards[args.warmup + i]) for i in range(args.steps)]
+    results = []
+    for i in range(args.steps):
+        results.append(run(shards[args.warmup + i]))
+        log(f"step {i}: {results[-1].stats['t_total_s']:.2f}s")
     ev1.record()
     fence()
     t_e2e = time.perf_counter() - t_start
@@ -270,7 +290,9 @@ def main():
 
     # ---- one extra profiled step: per-kernel-class device time (CUDA events on the
     #      engine stream) for the roofline numbers ----
+    log("timed region done; profiled step")
     prof = run(shards[-1], profile=True).stats
+    log("profiled step done")
     kms = prof["kernel_ms"]
     tot_ms = sum(kms.values()) or 1.0
     gemm_tf = prof["gemm_flops"] / (kms["gemm"] * 1e-3) / 1e12 if kms["gemm"] else 0.0
@@ -290,11 +312,14 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
+            log("cpu baseline: copying weights to host")
             hf_w = MS.unpack_to_hf(spec, weights)
+            log("cpu baseline: running oracle")
             cpu = cpu_baseline(spec, hf_w, vocab, shards[-1][:args.cpu_rows], os.cpu_count() or 1)
             # the same rows through the engine: the checker's verdict travels with the number
             got = run(shards[-1][:args.cpu_rows]).outputs
             cpu["engine_outputs_sample"] = got[:3]
+            log(f"cpu baseline done: {cpu['value']:.3f} rows/s")
         except Exception as e:  # the baseline must not sink the benchmark line
             cpu = {"value": None, "unit": "rows/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"failed: {e!r}"}

@@ -23,7 +23,7 @@ constexpr int kPfStageBytes = 2 * kTileBytes;
 constexpr int kPfSmem = kPfStages * kPfStageBytes + 1024;
 
 template <int G>
-__global__ void __launch_bounds__(kPfWarps * 32)
+__global__ void __launch_bounds__(kPfWarps * 32, 2)
 attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                     const __nv_bfloat16* __restrict__ kv_layer,
                     const int32_t* __restrict__ page_table, int max_pages,

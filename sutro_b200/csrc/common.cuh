@@ -207,6 +207,63 @@ SB_DEVICE void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
+// ---- cta_group::2 (CTA pair) variants ------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the even CTA
+
+SB_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+SB_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-CTA TMA load: data lands in this CTA's smem, bytes are counted on the leader's barrier.
+SB_DEVICE void tma_load_2d_cta2(uint32_t smem_dst, const CUtensorMap* m, uint32_t leader_bar,
+                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+SB_DEVICE void tmem_alloc_cta2(uint32_t smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_result),
+               "r"(ncols)
+               : "memory");
+}
+SB_DEVICE void tmem_relinquish_cta2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+SB_DEVICE void tmem_dealloc_cta2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+SB_DEVICE void tc_mma_f16_cta2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit: arrive on the barrier at this offset in every CTA of `mask`
+SB_DEVICE void tc_commit_cta2_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+SB_DEVICE void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+
 // K-major, 128-byte-swizzled operand tile: rows at 128 B pitch, 8-row groups
 // every 1024 B (SBO), descriptor version 1 (Blackwell), layout SWIZZLE_128B.
 // (cf. cute::UMMA::SmemDescriptor bit layout.)

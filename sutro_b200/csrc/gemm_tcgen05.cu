@@ -22,6 +22,7 @@
 //   SWIGLU_BF16    D[:, j] = bf16(silu(bf16(acc[2j])) * bf16(acc[2j+1]))
 //                  (gate/up weights interleaved row-wise; output has N/2 columns)
 //   STORE_F32      D = acc                             (lm_head logits)
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -49,6 +50,60 @@ struct GemmCfg {
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +align slack
 };
+
+// One thread's 32 consecutive accumulator columns of one row -> fused epilogue -> global.
+template <int EPI>
+SB_DEVICE void epilogue_store(const uint32_t (&v)[32], void* __restrict__ d_out,
+                              const __nv_bfloat16* __restrict__ resid, int row, int col0, int ldd) {
+  if constexpr (EPI == EPI_STORE_F32) {
+    float* dp = reinterpret_cast<float*>(d_out) + static_cast<size_t>(row) * ldd + col0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      st_v4(dp + 4 * i, make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+  } else if constexpr (EPI == EPI_SWIGLU_BF16) {
+    __nv_bfloat16* dp =
+        reinterpret_cast<__nv_bfloat16*>(d_out) + static_cast<size_t>(row) * ldd + (col0 >> 1);
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float r2[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float g = bf16_round(__uint_as_float(v[4 * i + 2 * h]));
+        const float u = bf16_round(__uint_as_float(v[4 * i + 2 * h + 1]));
+        const float s = bf16_round(g / (1.0f + __expf(-g)));
+        r2[h] = s * u;
+      }
+      o[i] = pack_bf16x2(r2[0], r2[1]);
+    }
+    st_v4(dp, make_uint4(o[0], o[1], o[2], o[3]));
+    st_v4(dp + 8, make_uint4(o[4], o[5], o[6], o[7]));
+  } else {
+    __nv_bfloat16* dp =
+        reinterpret_cast<__nv_bfloat16*>(d_out) + static_cast<size_t>(row) * ldd + col0;
+    uint32_t o[16];
+    if constexpr (EPI == EPI_RESIDUAL_BF16) {
+      const __nv_bfloat16* rp = resid + static_cast<size_t>(row) * ldd + col0;
+      uint4 rv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rv[i] = *reinterpret_cast<const uint4*>(rp + 8 * i);
+      const uint32_t* ru = reinterpret_cast<const uint32_t*>(rv);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 r = unpack_bf16x2(ru[i]);
+        o[i] = pack_bf16x2(bf16_round(__uint_as_float(v[2 * i])) + r.x,
+                           bf16_round(__uint_as_float(v[2 * i + 1])) + r.y);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        o[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      st_v4(dp + 8 * i, make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+  }
+}
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -179,54 +234,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
         tmem_ld_wait();
         const int col0 = n_blk * BLOCK_N + c * 32;
         if (!row_ok || col0 >= N) continue;
-        if constexpr (EPI == EPI_STORE_F32) {
-          float* dp = reinterpret_cast<float*>(d_out) + static_cast<size_t>(row) * ldd + col0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            st_v4(dp + 4 * i, make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
-        } else if constexpr (EPI == EPI_SWIGLU_BF16) {
-          __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(d_out) +
-                              static_cast<size_t>(row) * ldd + (col0 >> 1);
-          uint32_t o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float r2[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float g = bf16_round(__uint_as_float(v[4 * i + 2 * h]));
-              const float u = bf16_round(__uint_as_float(v[4 * i + 2 * h + 1]));
-              const float s = bf16_round(g / (1.0f + __expf(-g)));
-              r2[h] = s * u;
-            }
-            o[i] = pack_bf16x2(r2[0], r2[1]);
-          }
-          st_v4(dp, make_uint4(o[0], o[1], o[2], o[3]));
-          st_v4(dp + 8, make_uint4(o[4], o[5], o[6], o[7]));
-        } else {
-          __nv_bfloat16* dp =
-              reinterpret_cast<__nv_bfloat16*>(d_out) + static_cast<size_t>(row) * ldd + col0;
-          uint32_t o[16];
-          if constexpr (EPI == EPI_RESIDUAL_BF16) {
-            const __nv_bfloat16* rp = resid + static_cast<size_t>(row) * ldd + col0;
-            uint4 rv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rv[i] = *reinterpret_cast<const uint4*>(rp + 8 * i);
-            const uint32_t* ru = reinterpret_cast<const uint32_t*>(rv);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 r = unpack_bf16x2(ru[i]);
-              o[i] = pack_bf16x2(bf16_round(__uint_as_float(v[2 * i])) + r.x,
-                                 bf16_round(__uint_as_float(v[2 * i + 1])) + r.y);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              o[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            st_v4(dp + 8 * i, make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
-        }
+        epilogue_store<EPI>(v, d_out, resid, row, col0, ldd);
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -242,6 +250,177 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a 2-CTA cluster computes a 256x256 tile.
+// Each CTA stages its own 128 rows of A and its own 128 of the tile's 256 W rows
+// (so per-SM shared-memory fill traffic is 32 KiB per k-block instead of 48 KiB and
+// the tensor core reads half of B from the peer SM); the leader CTA's MMA warp issues
+// tcgen05.mma.cta_group::2 with M=256, N=256 and both CTAs' TMEM receive their 128
+// accumulator rows.  Barrier protocol:
+//   full[s]   leader only; both CTAs' TMA loads complete_tx on the leader's barrier
+//   empty[s]  per CTA; freed by a multicast tcgen05.commit
+//   tfull[a]  per CTA; multicast commit after the last k-block of a tile
+//   tempty[a] leader only; every epilogue warp of both CTAs arrives (count 8)
+// ---------------------------------------------------------------------------
+constexpr int k2Stages = 6;
+constexpr int k2HalfBytes = 128 * kBlockK * 2;      // 16 KiB: 128 rows x 64 bf16
+constexpr int k2StageBytes = 2 * k2HalfBytes;       // A half-tile + B half-tile per CTA
+constexpr int k2BlockN = 256;
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 256 + 1024;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
+                     const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
+                     const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd) {
+  extern __shared__ uint8_t smem_raw[];
+  // both CTAs of the pair must compute the same offsets: the dynamic smem base is the
+  // same in every CTA of a kernel, so the alignment fix-up below is identical too.
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + k2Stages;
+  uint64_t* tfull_bar = bars + 2 * k2Stages;
+  uint64_t* tempty_bar = bars + 2 * k2Stages + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * k2Stages + 2 * kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < kAccStages; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_cta2(smem_u32(tmem_slot), 2 * k2BlockN);
+    tmem_relinquish_cta2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + 255) / 256;
+  const int num_n = (N + k2BlockN - 1) / k2BlockN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = K / kBlockK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile % num_m;
+        const int n_blk = tile / num_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb_leader = smem_u32(&full_bar[stage]) & kPeerBitMask;
+          const uint32_t sa = smem_u32(smem + stage * k2StageBytes);
+          if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * k2StageBytes);
+          tma_load_2d_cta2(sa, &tm_a, fb_leader, kb * kBlockK, m_blk * 256 + rank * 128);
+          tma_load_2d_cta2(sa + k2HalfBytes, &tm_b, fb_leader, kb * kBlockK,
+                           n_blk * k2BlockN + rank * 128);
+          if (++stage == k2Stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, k2BlockN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * k2BlockN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * k2StageBytes);
+            const uint64_t adesc = umma_desc_k_sw128(sa);
+            const uint64_t bdesc = umma_desc_k_sw128(sa + k2HalfBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              tc_mma_f16_cta2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            tc_commit_cta2_mc(smem_u32(&empty_bar[stage]), 0x3);
+            if (kb == num_k - 1) tc_commit_cta2_mc(smem_u32(&tfull_bar[acc]), 0x3);
+          }
+          __syncwarp();
+          if (++stage == k2Stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue (both CTAs: each drains its own 128 accumulator rows) =====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile % num_m;
+      const int n_blk = tile / num_m;
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < k2BlockN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + acc * k2BlockN + c * 32 + (static_cast<uint32_t>(q * 32) << 16),
+                      v);
+        tmem_ld_wait();
+        const int col0 = n_blk * k2BlockN + c * 32;
+        if (!row_ok || col0 >= N) continue;
+        epilogue_store<EPI>(v, d_out, resid, row, col0, ldd);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & kPeerBitMask);
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cta2(tmem_base, 2 * k2BlockN);
   }
 }
 
@@ -352,9 +531,32 @@ int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* re
 }
 
 template <int EPI>
+int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* resid, int M, int N,
+                int K, int ldd, cudaStream_t stream) {
+  CUtensorMap tm_a, tm_b;
+  if (make_tmap(a, a_rows, K, 128, &tm_a)) return -1;
+  if (make_tmap(w, N, K, 128, &tm_b)) return -1;
+  auto kern = gemm2_bf16_tn_kernel<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SB_CUDA_CHECK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((M + 255) / 256) * ((N + k2BlockN - 1) / k2BlockN);
+  const int clusters = std::min(tiles, num_sms() / 2);
+  kern<<<2 * clusters, kGemmThreads, k2SmemBytes, stream>>>(
+      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI>
 int launch_epi(int block_n, const void* a, int a_rows, const void* w, void* d, const void* resid,
                int M, int N, int K, int ldd, cudaStream_t stream) {
   switch (block_n) {
+    case 512:  // CTA-pair kernel: 256x256 tile per 2-CTA cluster
+      return launch_cta2<EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
     case 64:
       return launch_cfg<64, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
     case 128:
@@ -367,18 +569,28 @@ int launch_epi(int block_n, const void* a, int a_rows, const void* w, void* d, c
 }  // namespace
 
 int gemm_pick_block_n(int M, int N) {
-  const int num_m = (M + kBlockM - 1) / kBlockM;
+  // Cost = waves x (tile area / efficiency); pick the cheapest configuration.
+  //   512: CTA-pair 256x256 per cluster (74 clusters)   64/128/256: one CTA, 128 x BLOCK_N
+  // Efficiencies are relative tensor-pipe rates measured for the tile shapes (the 1-CTA
+  // shapes are shared-memory-bandwidth limited: TMA fill + MMA operand reads).
   const int sms = num_sms();
-  // Largest tile that still gives every SM at least one tile; wide tiles
-  // amortise the A-operand shared-memory traffic, narrow ones fill the chip
-  // when the token batch is small.
-  for (int bn : {256, 128}) {
-    if (N % bn != 0 && N > bn) {
-      if (bn == 256 && N % 128 == 0) continue;  // prefer an exact tiling
+  double best = 1e30;
+  int pick = 128;
+  struct Cand { int id, tm, tn, units; double eff; };
+  const Cand cands[] = {{512, 256, 256, sms / 2, 2.0 * 1.00},
+                        {256, 128, 256, sms, 0.82},
+                        {128, 128, 128, sms, 0.70},
+                        {64, 128, 64, sms, 0.45}};
+  for (const Cand& c : cands) {
+    const long tiles = static_cast<long>((M + c.tm - 1) / c.tm) * ((N + c.tn - 1) / c.tn);
+    const long waves = (tiles + c.units - 1) / c.units;
+    const double cost = static_cast<double>(waves) * c.tm * c.tn / c.eff;
+    if (cost < best) {
+      best = cost;
+      pick = c.id;
     }
-    if (num_m * ((N + bn - 1) / bn) >= sms) return bn;
   }
-  return 64;
+  return pick;
 }
 
 int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* resid, int M,
@@ -389,8 +601,8 @@ int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* 
     return -1;
   }
   if (block_n == 0) block_n = gemm_pick_block_n(M, N);
-  if (block_n != 64 && block_n != 128 && block_n != 256) {
-    set_last_error("gemm_bf16_tn: block_n must be 64/128/256, got %d", block_n);
+  if (block_n != 64 && block_n != 128 && block_n != 256 && block_n != 512) {
+    set_last_error("gemm_bf16_tn: block_n must be 64/128/256/512(CTA pair), got %d", block_n);
     return -1;
   }
   switch (epilogue) {

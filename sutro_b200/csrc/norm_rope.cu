@@ -86,9 +86,18 @@ l2norm_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int 
   }
 }
 
-// One CTA per token, one warp per head (looping).  Lane l owns dims {2l, 2l+1}
-// and {64+2l, 64+2l+1}: the rotate-half partner of a dim lives in the same lane.
+// One CTA per token; a half-warp per head (two heads per warp pass).  Lane l' = lane % 16
+// owns dims {4l'..4l'+3} and {64+4l'..64+4l'+3}: the rotate-half partner of a dim lives in
+// the same lane, loads/stores are 8 bytes wide, the per-head reduction is 4 shuffles.
 constexpr int kRopeWarps = 8;
+
+SB_DEVICE void unpack4(const uint2& u, float (&f)[4]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  f[0] = a.x, f[1] = a.y, f[2] = b.x, f[3] = b.y;
+}
+SB_DEVICE uint2 pack4(const float (&f)[4]) {
+  return make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+}
 
 __global__ void __launch_bounds__(kRopeWarps * 32)
 rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ q_norm_w,
@@ -97,8 +106,8 @@ rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict_
                const int32_t* __restrict__ tok_pos, const int32_t* __restrict__ page_table,
                int max_pages, __nv_bfloat16* __restrict__ kv_layer, int hq, int hkv, float eps) {
   const int t = blockIdx.x;
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
+  const int half = threadIdx.x >> 4;       // half-warp index within the CTA: 0..15
+  const int l = threadIdx.x & 15;
   const int pos = tok_pos[t];
   const int slot = tok_slot[t];
   const int page = page_table[static_cast<size_t>(slot) * max_pages + pos / kPageTokens];
@@ -106,57 +115,64 @@ rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict_
   const int nheads = hq + 2 * hkv;
   __nv_bfloat16* row = qkv + static_cast<size_t>(t) * nheads * kHeadDim;
 
-  // cos/sin tables: [max_pos, 64] bf16 (already rounded like the reference does).
-  const float2 cs_c = __bfloat1622float2(
-      *reinterpret_cast<const __nv_bfloat162*>(cos_t + static_cast<size_t>(pos) * 64 + 2 * lane));
-  const float2 cs_s = __bfloat1622float2(
-      *reinterpret_cast<const __nv_bfloat162*>(sin_t + static_cast<size_t>(pos) * 64 + 2 * lane));
+  float cs[4], sn[4];  // cos/sin tables: [max_pos, 64] bf16, rounded like the reference
+  unpack4(*reinterpret_cast<const uint2*>(cos_t + static_cast<size_t>(pos) * 64 + 4 * l), cs);
+  unpack4(*reinterpret_cast<const uint2*>(sin_t + static_cast<size_t>(pos) * 64 + 4 * l), sn);
 
-  for (int h = warp; h < nheads; h += kRopeWarps) {
-    __nv_bfloat16* hp = row + h * kHeadDim;
-    float2 lo = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(hp + 2 * lane));
-    float2 hi = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(hp + 64 + 2 * lane));
-    const bool is_q = h < hq;
-    const bool is_k = !is_q && h < hq + hkv;
-    if (is_q || is_k) {
-      const __nv_bfloat16* nw = is_q ? q_norm_w : k_norm_w;
-      if (nw != nullptr) {
-        float ss = lo.x * lo.x + lo.y * lo.y + hi.x * hi.x + hi.y * hi.y;
-        ss = warp_sum(ss);
-        const float rstd = rsqrtf(ss / static_cast<float>(kHeadDim) + eps);
-        const float2 wl =
-            __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(nw + 2 * lane));
-        const float2 wh =
-            __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(nw + 64 + 2 * lane));
-        lo.x = bf16_round(wl.x * bf16_round(lo.x * rstd));
-        lo.y = bf16_round(wl.y * bf16_round(lo.y * rstd));
-        hi.x = bf16_round(wh.x * bf16_round(hi.x * rstd));
-        hi.y = bf16_round(wh.y * bf16_round(hi.y * rstd));
+  // every half-warp runs the same number of iterations (shuffles need full participation)
+  const int iters = (nheads + 2 * kRopeWarps - 1) / (2 * kRopeWarps);
+  for (int it = 0; it < iters; ++it) {
+    const int h = it * 2 * kRopeWarps + half;
+    const bool valid = h < nheads;
+    const int hh = valid ? h : 0;
+    __nv_bfloat16* hp = row + hh * kHeadDim;
+    float lo[4], hi[4];
+    unpack4(*reinterpret_cast<const uint2*>(hp + 4 * l), lo);
+    unpack4(*reinterpret_cast<const uint2*>(hp + 64 + 4 * l), hi);
+    const bool is_q = hh < hq;
+    const bool is_k = !is_q && hh < hq + hkv;
+    const __nv_bfloat16* nw = is_q ? q_norm_w : (is_k ? k_norm_w : nullptr);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ss += lo[i] * lo[i] + hi[i] * hi[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);  // 16-lane sum
+    if (nw != nullptr) {
+      const float rstd = rsqrtf(ss / static_cast<float>(kHeadDim) + eps);
+      float wl[4], wh[4];
+      unpack4(*reinterpret_cast<const uint2*>(nw + 4 * l), wl);
+      unpack4(*reinterpret_cast<const uint2*>(nw + 64 + 4 * l), wh);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        lo[i] = bf16_round(wl[i] * bf16_round(lo[i] * rstd));
+        hi[i] = bf16_round(wh[i] * bf16_round(hi[i] * rstd));
       }
-      // out[i]    = x[i]*cos - x[i+64]*sin ; out[i+64] = x[i+64]*cos + x[i]*sin
-      float2 olo, ohi;
-      olo.x = bf16_round(lo.x * cs_c.x) + bf16_round(-hi.x * cs_s.x);
-      olo.y = bf16_round(lo.y * cs_c.y) + bf16_round(-hi.y * cs_s.y);
-      ohi.x = bf16_round(hi.x * cs_c.x) + bf16_round(lo.x * cs_s.x);
-      ohi.y = bf16_round(hi.y * cs_c.y) + bf16_round(lo.y * cs_s.y);
-      lo = olo;
-      hi = ohi;
     }
-    const __nv_bfloat162 plo = __floats2bfloat162_rn(lo.x, lo.y);
-    const __nv_bfloat162 phi = __floats2bfloat162_rn(hi.x, hi.y);
+    if (is_q || is_k) {
+      // out[i] = x[i]*cos - x[i+64]*sin ; out[i+64] = x[i+64]*cos + x[i]*sin (bf16 op by op)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = bf16_round(lo[i] * cs[i]) + bf16_round(-hi[i] * sn[i]);
+        const float b = bf16_round(hi[i] * cs[i]) + bf16_round(lo[i] * sn[i]);
+        lo[i] = a;
+        hi[i] = b;
+      }
+    }
+    if (!valid) continue;
+    const uint2 plo = pack4(lo), phi = pack4(hi);
     if (is_q) {
-      *reinterpret_cast<__nv_bfloat162*>(hp + 2 * lane) = plo;
-      *reinterpret_cast<__nv_bfloat162*>(hp + 64 + 2 * lane) = phi;
+      *reinterpret_cast<uint2*>(hp + 4 * l) = plo;
+      *reinterpret_cast<uint2*>(hp + 64 + 4 * l) = phi;
     } else {
-      const int kvh = is_k ? (h - hq) : (h - hq - hkv);
+      const int kvh = is_k ? (hh - hq) : (hh - hq - hkv);
       __nv_bfloat16* tile = kv_layer +
                             (static_cast<size_t>(page) * hkv + kvh) * (2 * kTileElems) +
                             (is_k ? 0 : kTileElems) + r * kHeadDim;
-      const int c_lo = lane >> 2;  // 16-byte chunk of dims 2l..2l+1
+      const int c_lo = l >> 1;             // 16-byte chunk holding dims 4l..4l+3
       const int c_hi = c_lo + 8;
-      const int within = (2 * lane) & 7;
-      *reinterpret_cast<__nv_bfloat162*>(tile + ((c_lo ^ (r & 7)) << 3) + within) = plo;
-      *reinterpret_cast<__nv_bfloat162*>(tile + ((c_hi ^ (r & 7)) << 3) + within) = phi;
+      const int within = (4 * l) & 7;      // 0 or 4 elements into the chunk
+      *reinterpret_cast<uint2*>(tile + ((c_lo ^ (r & 7)) << 3) + within) = plo;
+      *reinterpret_cast<uint2*>(tile + ((c_hi ^ (r & 7)) << 3) + within) = phi;
     }
   }
 }

@@ -42,7 +42,7 @@ def _gemm(a, w, epi=0, resid=None, block_n=0, m=None, out=None):
     return out
 
 
-@pytest.mark.parametrize("block_n", [64, 128, 256, 0])
+@pytest.mark.parametrize("block_n", [64, 128, 256, 512, 0])  # 512 = CTA-pair kernel
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (300, 768, 512),
                                    (1000, 1536, 2560), (77, 32 * 11, 192)])
 def test_gemm_store_bf16(M, N, K, block_n):
@@ -81,6 +81,26 @@ def test_gemm_a_rows_larger_than_m():
     assert torch.all(out[M:] == 7.0)  # rows past M untouched
 
 
+@pytest.mark.parametrize("epi", [1, 2])
+def test_gemm_cta_pair_fused_epilogues(epi):
+    """residual / SwiGLU epilogues through the cta_group::2 kernel at a multi-wave shape."""
+    M, N, K = 1500, 5120, 1024
+    torch.manual_seed(7)
+    a = bf(torch.randn(M, K, device=DEV))
+    w = bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
+    acc = a.float() @ w.float().t()
+    if epi == 1:
+        r = bf(torch.randn(M, N, device=DEV))
+        out = r.clone()
+        _gemm(a, w, 1, resid=out, out=out, block_n=512)
+        ref = bf(bf(acc).float() + r.float())
+    else:
+        out = _gemm(a, w, 2, block_n=512)
+        g, u = bf(acc[:, 0::2]).float(), bf(acc[:, 1::2]).float()
+        ref = bf(bf(torch.nn.functional.silu(g)).float() * u)
+    assert torch.allclose(out.float(), ref.float(), rtol=3e-2, atol=3e-2)
+
+
 def test_gemm_residual():
     M, N, K = 260, 768, 512
     torch.manual_seed(3)
@@ -113,7 +133,7 @@ def test_gemm_f32_logits_partial_n_tile():
     torch.manual_seed(5)
     a = bf(torch.randn(M, K, device=DEV))
     w = bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
-    for bn in (64, 128, 256):
+    for bn in (64, 128, 256, 512):
         d = _gemm(a, w, 3, block_n=bn)
         ref = a.float() @ w.float().t()
         assert torch.allclose(d, ref, rtol=1e-3, atol=1e-3), bn

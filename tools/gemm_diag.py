@@ -55,7 +55,8 @@ def run(M, N, K, bn, epi=3):
 if __name__ == "__main__":
     torch.cuda.init()
     for (M, N, K, bn) in [(128, 64, 64, 64), (128, 128, 64, 128), (128, 256, 64, 256),
-                          (128, 256, 128, 256), (256, 512, 256, 256), (300, 768, 512, 128)]:
+                          (128, 256, 128, 256), (256, 512, 256, 256), (300, 768, 512, 128),
+                          (256, 256, 64, 512), (256, 256, 256, 512), (600, 1024, 512, 512)]:
         try:
             run(M, N, K, bn)
         except Exception as e:  # noqa: BLE001
