@@ -51,6 +51,21 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +align slack
 };
 
+// Tile rasterisation: consecutive tile ids sweep all N tiles of a group of GM row-tiles
+// before moving on, so the CTAs running concurrently share a [GM*128, K] slab of A and a
+// ~148/GM-tile slab of W that both fit in the 126 MB L2.  (M-fastest order re-read A from
+// HBM once per N tile: 5x the algorithmic traffic on the down projection, ncu r01.)
+template <int GM>
+SB_DEVICE void tile_to_mn(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int group_tiles = GM * num_n;
+  const int g = tile / group_tiles;
+  const int first_m = g * GM;
+  const int gm = min(GM, num_m - first_m);
+  const int within = tile - g * group_tiles;
+  m_blk = first_m + within % gm;
+  n_blk = within / gm;
+}
+
 // One thread's 32 consecutive accumulator columns of one row -> fused epilogue -> global.
 template <int EPI>
 SB_DEVICE void epilogue_store(const uint32_t (&v)[32], void* __restrict__ d_out,
@@ -160,8 +175,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m;
-        const int n_blk = tile / num_m;
+        int m_blk, n_blk;
+        tile_to_mn<16>(tile, num_m, num_n, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -220,8 +235,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % num_m;
-      const int n_blk = tile / num_m;
+      int m_blk, n_blk;
+      tile_to_mn<16>(tile, num_m, num_n, m_blk, n_blk);
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       const int row = m_blk * kBlockM + q * 32 + lane;
@@ -330,8 +345,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile % num_m;
-        const int n_blk = tile / num_m;
+        int m_blk, n_blk;
+        tile_to_mn<8>(tile, num_m, num_n, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb_leader = smem_u32(&full_bar[stage]) & kPeerBitMask;
@@ -390,8 +405,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = tile % num_m;
-      const int n_blk = tile / num_m;
+      int m_blk, n_blk;
+      tile_to_mn<8>(tile, num_m, num_n, m_blk, n_blk);
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       const int row = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
