@@ -47,9 +47,11 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, fast: bool = False) -> torch.Tensor:
-    """bf16 x bf16 -> fp32 accumulate -> bf16 (returned as fp32 holding bf16 values)."""
-    if fast:  # oneDNN bf16 GEMM: same contract, much faster on the big CPU-baseline model
-        return F.linear(x.to(BF), w).float()
+    """bf16 x bf16 -> fp32 accumulate -> bf16 (returned as fp32 holding bf16 values).
+    `fast`: the weight was pre-converted to fp32 once (RefModel(fast=True)), so the product
+    is a plain sgemm — the same contract without re-converting 8 GB of weights per call."""
+    if fast:
+        return _r(x @ w.t())
     return _r(x.float() @ w.float().t())
 
 
@@ -75,8 +77,11 @@ class RefModel:
     def __init__(self, spec, weights: Dict[str, torch.Tensor], fast: bool = False):
         from sutro_b200.modelspec import rope_tables
         self.spec = spec
-        self.w = weights
         self.fast = fast
+        if fast:  # big-model CPU baseline: keep every matrix in fp32 (bf16 values) up front
+            weights = {k: (v.float() if v.dim() == 2 and "embed_tokens" not in k else v)
+                       for k, v in weights.items()}
+        self.w = weights
         self.cos, self.sin = rope_tables(spec)
         self._lm = None
 
