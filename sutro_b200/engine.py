@@ -335,6 +335,11 @@ class LocalEngine:
         # ---- phase A -------------------------------------------------------------
         data, off = rows_to_blob(rows)
         n_rows, n_bytes = len(off) - 1, int(off[-1])
+        if n_rows == 0:
+            return GenerationResult([] if not emb_mode else None, [] if return_tokens else None,
+                                    np.zeros((0, self.spec.d_model), np.float32) if emb_mode
+                                    else None, {"n_rows": 0, "input_tokens": 0,
+                                                "output_tokens": 0, "rows_done": 0})
         pre, suf = self._template_tokens(system_prompt)
         dfa = self.compile_schema(json_schema, fsm_limits) if json_schema is not None else None
         with torch.cuda.device(dev):

@@ -187,6 +187,14 @@ def test_max_new_tokens_truncates_and_eos_stops():
         eng.generate([long_row], max_new_tokens=4, truncate_rows=False)
 
 
+def test_empty_and_null_inputs():
+    spec, w, v, eng = build("tiny-qwen3", max_slots=4, max_prefill_tokens=256)
+    assert eng.generate([], max_new_tokens=4).outputs == []
+    res = eng.generate([None, "", "a"], max_new_tokens=2, ignore_eos=True, return_tokens=True)
+    assert len(res.outputs) == 3 and all(len(t) == 2 for t in res.out_tokens)
+    assert res.out_tokens[0] == res.out_tokens[1]        # null is the empty string
+
+
 def test_embedding_model_matches_oracle():
     spec, w, v, eng = build("tiny-qwen3-embedding", max_slots=8, max_prefill_tokens=256)
     rows = synth.short_texts(20, seed=3)
