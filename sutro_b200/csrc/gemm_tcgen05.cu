@@ -280,13 +280,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
 //   tfull[a]  per CTA; multicast commit after the last k-block of a tile
 //   tempty[a] leader only; every epilogue warp of both CTAs arrives (count 8)
 // ---------------------------------------------------------------------------
-constexpr int k2Stages = 6;
 constexpr int k2HalfBytes = 128 * kBlockK * 2;      // 16 KiB: 128 rows x 64 bf16
 constexpr int k2StageBytes = 2 * k2HalfBytes;       // A half-tile + B half-tile per CTA
 constexpr int k2BlockN = 256;
-constexpr int k2SmemBytes = k2Stages * k2StageBytes + 256 + 1024;
+constexpr int k2SmemBytes(int stages) { return stages * k2StageBytes + 256 + 1024; }
 
-template <int EPI>
+template <int EPI, int k2Stages>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
                      const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
@@ -545,22 +544,22 @@ int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* re
   return 0;
 }
 
-template <int EPI>
+template <int EPI, int STAGES>
 int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* resid, int M, int N,
                 int K, int ldd, cudaStream_t stream) {
   CUtensorMap tm_a, tm_b;
   if (make_tmap(a, a_rows, K, 128, &tm_a)) return -1;
   if (make_tmap(w, N, K, 128, &tm_b)) return -1;
-  auto kern = gemm2_bf16_tn_kernel<EPI>;
+  auto kern = gemm2_bf16_tn_kernel<EPI, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA_CHECK(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       k2SmemBytes(STAGES)));
     attr_set = true;
   }
   const int tiles = ((M + 255) / 256) * ((N + k2BlockN - 1) / k2BlockN);
   const int clusters = std::min(tiles, num_sms() / 2);
-  kern<<<2 * clusters, kGemmThreads, k2SmemBytes, stream>>>(
+  kern<<<2 * clusters, kGemmThreads, k2SmemBytes(STAGES), stream>>>(
       tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -571,7 +570,11 @@ int launch_epi(int block_n, const void* a, int a_rows, const void* w, void* d, c
                int M, int N, int K, int ldd, cudaStream_t stream) {
   switch (block_n) {
     case 512:  // CTA-pair kernel: 256x256 tile per 2-CTA cluster
-      return launch_cta2<EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_cta2<EPI, 7>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+    case 516:  // experiment knobs (tools/gemm_bench.py): same kernel, shallower rings
+      return launch_cta2<EPI, 6>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+    case 514:
+      return launch_cta2<EPI, 4>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
     case 64:
       return launch_cfg<64, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
     case 128:
@@ -616,7 +619,8 @@ int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* 
     return -1;
   }
   if (block_n == 0) block_n = gemm_pick_block_n(M, N);
-  if (block_n != 64 && block_n != 128 && block_n != 256 && block_n != 512) {
+  if (block_n != 64 && block_n != 128 && block_n != 256 && block_n != 512 && block_n != 514 &&
+      block_n != 516) {
     set_last_error("gemm_bf16_tn: block_n must be 64/128/256/512(CTA pair), got %d", block_n);
     return -1;
   }

@@ -16,6 +16,9 @@ namespace {
 
 constexpr int kRowWarps = 4;
 
+// NV = 16-byte vectors per lane held in registers (row length <= NV*32*8 elements): the row
+// is read from HBM exactly once.  NV == 0 is the generic two-pass fallback for long rows.
+template <int NV>
 __global__ void __launch_bounds__(kRowWarps * 32)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                __nv_bfloat16* __restrict__ out, int rows, int d, float eps) {
@@ -27,19 +30,15 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
   uint4* orow = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * d);
   const int nvec = d >> 3;
   float ss = 0.f;
-  for (int i = lane; i < nvec; i += 32) {
-    const uint4 v = xr[i];
+  auto sq = [&](const uint4& v) {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = unpack_bf16x2(u[j]);
       ss += f.x * f.x + f.y * f.y;
     }
-  }
-  ss = warp_sum(ss);
-  const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
-  for (int i = lane; i < nvec; i += 32) {
-    const uint4 v = xr[i];  // second touch hits L1/L2
+  };
+  auto emit = [&](int i, const uint4& v, float rstd) {
     const uint4 g = wr[i];
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
@@ -51,6 +50,28 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
       o[j] = pack_bf16x2(wv.x * bf16_round(f.x * rstd), wv.y * bf16_round(f.y * rstd));
     }
     orow[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  if constexpr (NV > 0) {
+    uint4 v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      v[k] = (i < nvec) ? ld_nc_v4(xr + i) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sq(v[k]);
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int i = lane + 32 * k;
+      if (i < nvec) emit(i, v[k], rstd);
+    }
+  } else {
+    for (int i = lane; i < nvec; i += 32) sq(xr[i]);
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
+    for (int i = lane; i < nvec; i += 32) emit(i, xr[i], rstd);  // second touch hits L1/L2
   }
 }
 
@@ -119,16 +140,33 @@ rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict_
   unpack4(*reinterpret_cast<const uint2*>(cos_t + static_cast<size_t>(pos) * 64 + 4 * l), cs);
   unpack4(*reinterpret_cast<const uint2*>(sin_t + static_cast<size_t>(pos) * 64 + 4 * l), sn);
 
-  // every half-warp runs the same number of iterations (shuffles need full participation)
+  // Every half-warp runs the same number of iterations (shuffles need full participation).
+  // All of this thread's loads are issued before the first in-place store, so the memory
+  // system sees up to 2*kMaxIt independent 8-byte requests per thread instead of a
+  // load -> compute -> store chain per head.
+  constexpr int kMaxIt = 4;  // supports up to 64 heads (q + k + v) per token
   const int iters = (nheads + 2 * kRopeWarps - 1) / (2 * kRopeWarps);
-  for (int it = 0; it < iters; ++it) {
+  uint2 rlo[kMaxIt], rhi[kMaxIt];
+#pragma unroll
+  for (int it = 0; it < kMaxIt; ++it) {
+    const int h = it * 2 * kRopeWarps + half;
+    if (it < iters && h < nheads) {
+      rlo[it] = *reinterpret_cast<const uint2*>(row + h * kHeadDim + 4 * l);
+      rhi[it] = *reinterpret_cast<const uint2*>(row + h * kHeadDim + 64 + 4 * l);
+    } else {
+      rlo[it] = rhi[it] = make_uint2(0u, 0u);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kMaxIt; ++it) {
+    if (it >= iters) break;
     const int h = it * 2 * kRopeWarps + half;
     const bool valid = h < nheads;
     const int hh = valid ? h : 0;
     __nv_bfloat16* hp = row + hh * kHeadDim;
     float lo[4], hi[4];
-    unpack4(*reinterpret_cast<const uint2*>(hp + 4 * l), lo);
-    unpack4(*reinterpret_cast<const uint2*>(hp + 64 + 4 * l), hi);
+    unpack4(rlo[it], lo);
+    unpack4(rhi[it], hi);
     const bool is_q = hh < hq;
     const bool is_k = !is_q && hh < hq + hkv;
     const __nv_bfloat16* nw = is_q ? q_norm_w : (is_k ? k_norm_w : nullptr);
@@ -186,9 +224,21 @@ int rmsnorm(const void* x, const void* w, void* out, int rows, int d, float eps,
     set_last_error("rmsnorm: d=%d must be a multiple of 8", d);
     return -1;
   }
-  rmsnorm_kernel<<<(rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
-      static_cast<__nv_bfloat16*>(out), rows, d, eps);
+  const int nvec = d >> 3;
+  const dim3 grid((rows + kRowWarps - 1) / kRowWarps), block(kRowWarps * 32);
+  auto* xp = static_cast<const __nv_bfloat16*>(x);
+  auto* wp = static_cast<const __nv_bfloat16*>(w);
+  auto* op = static_cast<__nv_bfloat16*>(out);
+  if (x == out)  // in place: the streaming (non-coherent) loads must not be used
+    rmsnorm_kernel<0><<<grid, block, 0, stream>>>(xp, wp, op, rows, d, eps);
+  else if (nvec <= 32 * 4)
+    rmsnorm_kernel<4><<<grid, block, 0, stream>>>(xp, wp, op, rows, d, eps);
+  else if (nvec <= 32 * 10)
+    rmsnorm_kernel<10><<<grid, block, 0, stream>>>(xp, wp, op, rows, d, eps);
+  else if (nvec <= 32 * 16)
+    rmsnorm_kernel<16><<<grid, block, 0, stream>>>(xp, wp, op, rows, d, eps);
+  else
+    rmsnorm_kernel<0><<<grid, block, 0, stream>>>(xp, wp, op, rows, d, eps);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -224,6 +274,10 @@ int rope_kv_write(void* qkv, const void* q_norm_w, const void* k_norm_w, const v
                   const int32_t* page_table, int max_pages, void* kv_layer, int T, int hq,
                   int hkv, float eps, cudaStream_t stream) {
   if (T <= 0) return 0;
+  if (hq + 2 * hkv > 64) {
+    set_last_error("rope_kv_write: at most 64 heads (q+k+v) per token, got %d", hq + 2 * hkv);
+    return -1;
+  }
   rope_kv_kernel<<<T, kRopeWarps * 32, 0, stream>>>(
       static_cast<__nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(q_norm_w),
       static_cast<const __nv_bfloat16*>(k_norm_w), static_cast<const __nv_bfloat16*>(cos_tab),
