@@ -229,7 +229,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="qwen-3-4b")
     ap.add_argument("--rows", type=int, default=20000, help="rows per GPU per step")
-    ap.add_argument("--max-slots", type=int, default=2048)
+    ap.add_argument("--max-slots", type=int, default=3584,
+                    help="decode slots; 3584 = 14 x 256 rows quantises the CTA-pair GEMM tiles well")
     ap.add_argument("--max-prefill-tokens", type=int, default=16384)
     ap.add_argument("--cpu-rows", type=int, default=8, help="max rows in the CPU-baseline sample")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0,
