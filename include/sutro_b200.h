@@ -68,6 +68,9 @@ int sb200_attn_decode(const void* qkv, void* out, const void* kv_layer, const in
                       int max_pages, const int32_t* row_slot, const int32_t* ctx_len, int B, int hq,
                       int hkv, float scale, void* stream);
 
+/* test hook: 0 = automatic choice, 1 = 4-warps-per-pair split kernel, 2 = warp-per-pair */
+void sb200_attn_decode_force_variant(int v);
+
 /* K3: causal varlen prefill attention over the paged cache. */
 int sb200_attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
                        int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,

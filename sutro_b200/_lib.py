@@ -29,6 +29,7 @@ _SIGNATURES = {
                                                      c_float, c_void_p]),
     "sb200_attn_decode": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                                    c_float, c_void_p]),
+    "sb200_attn_decode_force_variant": (None, [c_int]),
     "sb200_attn_prefill": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_int] + [c_void_p] * 4 +
                            [c_int, c_int, c_float, c_void_p]),
     "sb200_attn_prefill_q_tile": (c_int, [c_int, c_int]),

@@ -76,6 +76,8 @@ int sb200_attn_decode(const void* qkv, void* out, const void* kv_layer, const in
                      scale, STREAM(stream));
 }
 
+void sb200_attn_decode_force_variant(int v) { attn_decode_force_variant(v); }
+
 int sb200_attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
                        int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
                        const int32_t* seq_q_start, const int32_t* seq_q_len,

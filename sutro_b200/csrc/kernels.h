@@ -58,6 +58,8 @@ int attn_decode(const void* qkv, void* out, const void* kv_layer, const int32_t*
                 int max_pages, const int32_t* row_slot, const int32_t* ctx_len, int B, int hq,
                 int hkv, float scale, cudaStream_t stream);
 
+void attn_decode_force_variant(int v);  // 0 auto, 1 split kernel, 2 warp-per-pair kernel
+
 // K3 — causal prefill attention over the paged cache (varlen batch).
 // work: [n_work] {seq, q_tile_start}; per-seq arrays are indexed by seq.
 int attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,

@@ -259,8 +259,10 @@ def attn_ref(q, k, v, scale):
     return torch.einsum("hl,lhd->hd", p, vv)
 
 
+@pytest.mark.parametrize("variant", [1, 2])   # 1: 4-warp split kernel, 2: warp-per-pair kernel
 @pytest.mark.parametrize("hq,hkv", [(32, 8), (16, 8), (8, 8), (16, 2)])
-def test_attn_decode(hq, hkv):
+def test_attn_decode(hq, hkv, variant):
+    L.lib().sb200_attn_decode_force_variant(variant)
     torch.manual_seed(hq * 100 + hkv)
     lens = [1, 15, 16, 17, 63, 64, 65, 130, 257, 600]
     B = len(lens)
@@ -276,6 +278,7 @@ def test_attn_decode(hq, hkv):
     L.check(L.lib().sb200_attn_decode(L.ptr(qkv), L.ptr(out), L.ptr(pool), L.ptr(pt), max_pages,
                                       L.ptr(row_slot), L.ptr(ctx), B, hq, hkv, scale, stream()))
     torch.cuda.synchronize()
+    L.lib().sb200_attn_decode_force_variant(0)
     for b in range(B):
         s = B - 1 - b
         q = qkv[b].view(hq + 2 * hkv, KV.HD)[:hq]

@@ -88,19 +88,22 @@ def main():
     lim = FsmLimits(max_string_chars=12, max_array_items=3)
     t = time.time()
     res = eng.generate(rows, system_prompt="Extract the order as JSON.",
-                       json_schema=Order.model_json_schema(), max_new_tokens=128, fsm_limits=lim)
+                       json_schema=Order.model_json_schema(), max_new_tokens=160, fsm_limits=lim,
+                       return_tokens=True)
     dt = time.time() - t
-    ok = 0
-    for o in res.outputs:
+    ok = cut = 0
+    for o, toks in zip(res.outputs, res.out_tokens):
         try:
             Order.model_validate(json.loads(o))
             ok += 1
         except Exception:
-            pass
-    print(f"llama-3.1-8b nested schema: {len(rows) / dt:.0f} rows/s, {ok}/{len(rows)} outputs validate, "
+            assert len(toks) == 160, (o, len(toks))   # only the token cap may end a row early
+            cut += 1
+    print(f"llama-3.1-8b nested schema: {len(rows) / dt:.0f} rows/s, {ok}/{len(rows)} outputs validate "
+          f"({cut} cut by max_new_tokens), "
           f"fsm_states {res.stats['fsm_states']}, out tokens {res.stats['output_tokens']}")
     print("  sample:", res.outputs[0][:160])
-    assert ok >= len(rows) - 2   # rows cut by max_new_tokens may be incomplete
+    assert ok + cut == len(rows) and ok > len(rows) // 2
     print("real-size smoke ok")
 
 
