@@ -18,7 +18,7 @@ namespace sb {
 namespace {
 
 constexpr int kPfWarps = 8;
-constexpr int kPfStages = 8;  // deep ring: a CTA sees 5-40 pages; prefetch distance must cover L2/HBM latency
+constexpr int kPfStages = 4;
 constexpr int kPfStageBytes = 2 * kTileBytes;
 constexpr int kPfSmem = kPfStages * kPfStageBytes + 1024;
 

@@ -22,15 +22,13 @@ template <int NV>
 __global__ void __launch_bounds__(kRowWarps * 32)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                __nv_bfloat16* __restrict__ out, int rows, int d, float eps) {
+  const int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const uint4* wr = reinterpret_cast<const uint4*>(w);
-  const int nvec = d >> 3;
-  // grid-stride over rows: a few resident CTAs per SM stream many rows each instead of
-  // one short-lived CTA per 4 rows (CTA launch rate, not HBM, was the limiter)
-  for (int row = blockIdx.x * kRowWarps + (threadIdx.x >> 5); row < rows;
-       row += gridDim.x * kRowWarps) {
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * d);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
   uint4* orow = reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * d);
+  const int nvec = d >> 3;
   float ss = 0.f;
   auto sq = [&](const uint4& v) {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
@@ -74,7 +72,6 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
     ss = warp_sum(ss);
     const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
     for (int i = lane; i < nvec; i += 32) emit(i, xr[i], rstd);  // second touch hits L1/L2
-  }
   }
 }
 
@@ -128,11 +125,10 @@ rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict_
                const __nv_bfloat16* __restrict__ k_norm_w, const __nv_bfloat16* __restrict__ cos_t,
                const __nv_bfloat16* __restrict__ sin_t, const int32_t* __restrict__ tok_slot,
                const int32_t* __restrict__ tok_pos, const int32_t* __restrict__ page_table,
-               int max_pages, __nv_bfloat16* __restrict__ kv_layer, int T, int hq, int hkv,
-               float eps) {
+               int max_pages, __nv_bfloat16* __restrict__ kv_layer, int hq, int hkv, float eps) {
+  const int t = blockIdx.x;
   const int half = threadIdx.x >> 4;       // half-warp index within the CTA: 0..15
   const int l = threadIdx.x & 15;
-  for (int t = blockIdx.x; t < T; t += gridDim.x) {   // grid-stride: CTAs are persistent-ish
   const int pos = tok_pos[t];
   const int slot = tok_slot[t];
   const int page = page_table[static_cast<size_t>(slot) * max_pages + pos / kPageTokens];
@@ -217,7 +213,6 @@ rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict_
       *reinterpret_cast<uint2*>(tile + ((c_hi ^ (r & 7)) << 3) + within) = phi;
     }
   }
-  }
 }
 
 }  // namespace
@@ -230,8 +225,7 @@ int rmsnorm(const void* x, const void* w, void* out, int rows, int d, float eps,
     return -1;
   }
   const int nvec = d >> 3;
-  const int want = (rows + kRowWarps - 1) / kRowWarps;
-  const dim3 grid(want < 148 * 12 ? want : 148 * 12), block(kRowWarps * 32);
+  const dim3 grid((rows + kRowWarps - 1) / kRowWarps), block(kRowWarps * 32);
   auto* xp = static_cast<const __nv_bfloat16*>(x);
   auto* wp = static_cast<const __nv_bfloat16*>(w);
   auto* op = static_cast<__nv_bfloat16*>(out);
@@ -284,11 +278,11 @@ int rope_kv_write(void* qkv, const void* q_norm_w, const void* k_norm_w, const v
     set_last_error("rope_kv_write: at most 64 heads (q+k+v) per token, got %d", hq + 2 * hkv);
     return -1;
   }
-  rope_kv_kernel<<<T < 148 * 8 ? T : 148 * 8, kRopeWarps * 32, 0, stream>>>(
+  rope_kv_kernel<<<T, kRopeWarps * 32, 0, stream>>>(
       static_cast<__nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(q_norm_w),
       static_cast<const __nv_bfloat16*>(k_norm_w), static_cast<const __nv_bfloat16*>(cos_tab),
       static_cast<const __nv_bfloat16*>(sin_tab), tok_slot, tok_pos, page_table, max_pages,
-      static_cast<__nv_bfloat16*>(kv_layer), T, hq, hkv, eps);
+      static_cast<__nv_bfloat16*>(kv_layer), hq, hkv, eps);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
