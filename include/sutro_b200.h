@@ -47,6 +47,15 @@ int sb200_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total
 int sb200_gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* resid, int M,
                        int N, int K, int ldd, int epilogue, int block_n, void* stream);
 
+/* K1+K5 fused: qkv = A Wqkv^T with per-head q/k RMSNorm + RoPE + paged K/V write applied in
+ * the GEMM epilogue (same result as sb200_gemm_bf16_tn followed by sb200_rope_kv_write);
+ * q heads land in qkv_out[:, :hq*128], K/V go straight to the cache.  block_n: 0/128/256/512. */
+int sb200_gemm_qkv_rope(const void* a, int a_rows, const void* w, void* qkv_out, int M, int K,
+                        int block_n, const void* q_norm_w, const void* k_norm_w,
+                        const void* cos_tab, const void* sin_tab, const int32_t* tok_slot,
+                        const int32_t* tok_pos, const int32_t* page_table, int max_pages,
+                        void* kv_layer, int hq, int hkv, float eps, void* stream);
+
 /* K4: out = w * bf16(x * rsqrt(mean(x^2)+eps))  (transformers Qwen3RMSNorm) */
 int sb200_rmsnorm(const void* x, const void* w, void* out, int rows, int d, float eps,
                   void* stream);

@@ -22,6 +22,8 @@ _SIGNATURES = {
     "sb200_device_info": (c_int, [C.POINTER(c_int)] * 3 + [C.POINTER(c_size_t)]),
     "sb200_gemm_bf16_tn": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                    c_int, c_int, c_int, c_int, c_void_p]),
+    "sb200_gemm_qkv_rope": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int] +
+                            [c_void_p] * 7 + [c_int, c_void_p, c_int, c_int, c_float, c_void_p]),
     "sb200_rmsnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "sb200_embed_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "sb200_l2_normalize_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -47,6 +47,18 @@ int sb200_gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const 
   return gemm_bf16_tn(a, a_rows, w, d, resid, M, N, K, ldd, epilogue, block_n, STREAM(stream));
 }
 
+int sb200_gemm_qkv_rope(const void* a, int a_rows, const void* w, void* qkv_out, int M, int K,
+                        int block_n, const void* q_norm_w, const void* k_norm_w,
+                        const void* cos_tab, const void* sin_tab, const int32_t* tok_slot,
+                        const int32_t* tok_pos, const int32_t* page_table, int max_pages,
+                        void* kv_layer, int hq, int hkv, float eps, void* stream) {
+  QkvEpiArgs ea{tok_pos, tok_slot, page_table, max_pages, kv_layer, cos_tab, sin_tab,
+                q_norm_w, k_norm_w, hq, hkv, eps};
+  const int N = (hq + 2 * hkv) * kHeadDim;
+  return gemm_bf16_tn(a, a_rows, w, qkv_out, nullptr, M, N, K, N, EPI_QKV_ROPE, block_n,
+                      STREAM(stream), &ea);
+}
+
 int sb200_rmsnorm(const void* x, const void* w, void* out, int rows, int d, float eps,
                   void* stream) {
   return rmsnorm(x, w, out, rows, d, eps, STREAM(stream));

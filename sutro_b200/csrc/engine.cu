@@ -12,6 +12,7 @@
 // workspaces sized for max(max_prefill_tokens, max_slots) tokens, a logits
 // chunk, the page table and the per-slot decode state.
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -193,6 +194,7 @@ struct Engine {
   Profiler prof;
   double gemm_flops = 0, attn_decode_bytes = 0;
   int device = 0;
+  bool fuse_qkv = true;  // SB200_FUSE_QKV=0 keeps the separate rope_kv_write kernel (A/B tests)
 
   ~Engine() {
     for (void* p : {(void*)x, (void*)h, (void*)qkv, (void*)attn, (void*)act, (void*)hl, (void*)hn,
@@ -221,6 +223,7 @@ struct Engine {
     q_tile = attn_prefill_q_tile(c.n_q_heads, c.n_kv_heads);
     num_pages = c.num_pages;
     layer_stride = static_cast<size_t>(num_pages) * c.n_kv_heads * 2 * kTileElems;
+    if (const char* e = getenv("SB200_FUSE_QKV")) fuse_qkv = e[0] != '0';
     SB_CUDA_CHECK(cudaGetDevice(&device));
     SB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     const size_t T = t_max, S = c.max_slots + 2;  // +prefix slot, +dummy slot
@@ -271,11 +274,20 @@ struct Engine {
     SB_K(SB200_KC_EMBED, embed_gather(tok_ids, w.embed, x, T, c.d_model, stream));
     for (int l = 0; l < c.n_layers; ++l) {
       SB_K(SB200_KC_NORM, rmsnorm(x, ln1[l], h, T, c.d_model, c.rms_eps, stream));
-      SB_K(SB200_KC_GEMM, gemm(h, wqkv[l], qkv, nullptr, T, qkv_dim, c.d_model, qkv_dim,
-                               EPI_STORE_BF16));
-      SB_K(SB200_KC_ROPE,
-           rope_kv_write(qkv, qn[l], kn[l], w.rope_cos, w.rope_sin, tok_slot, tok_pos, page_table,
-                         max_pages, kv_layer(l), T, c.n_q_heads, c.n_kv_heads, c.rms_eps, stream));
+      if (fuse_qkv) {
+        // K1+K5 fused: q/k-norm, RoPE and the paged K/V write happen in the GEMM epilogue
+        QkvEpiArgs qa{tok_pos, tok_slot, page_table, max_pages, kv_layer(l), w.rope_cos,
+                      w.rope_sin, qn[l], kn[l], c.n_q_heads, c.n_kv_heads, c.rms_eps};
+        gemm_flops += 2.0 * T * qkv_dim * c.d_model;
+        SB_K(SB200_KC_GEMM, gemm_bf16_tn(h, t_max, wqkv[l], qkv, nullptr, T, qkv_dim, c.d_model,
+                                         qkv_dim, EPI_QKV_ROPE, 0, stream, &qa));
+      } else {
+        SB_K(SB200_KC_GEMM, gemm(h, wqkv[l], qkv, nullptr, T, qkv_dim, c.d_model, qkv_dim,
+                                 EPI_STORE_BF16));
+        SB_K(SB200_KC_ROPE, rope_kv_write(qkv, qn[l], kn[l], w.rope_cos, w.rope_sin, tok_slot,
+                                          tok_pos, page_table, max_pages, kv_layer(l), T,
+                                          c.n_q_heads, c.n_kv_heads, c.rms_eps, stream));
+      }
       if (prefill) {
         SB_K(SB200_KC_ATTN_PREFILL,
              attn_prefill(qkv, attn, kv_layer(l), page_table, max_pages, d_work, n_work,

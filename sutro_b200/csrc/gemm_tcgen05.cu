@@ -120,11 +120,133 @@ SB_DEVICE void epilogue_store(const uint32_t (&v)[32], void* __restrict__ d_out,
   }
 }
 
+// ---------------------------------------------------------------------------
+// EPI_QKV_ROPE: one thread owns one token row and, per 128-column head, applies exactly
+// what rope_kv_kernel (norm_rope.cu) does to the stored bf16 tensor — bf16 rounding of the
+// projection, optional per-head RMSNorm, rotate-half RoPE with bf16 op-by-op rounding —
+// then writes q heads to the qkv buffer and k/v heads straight into the swizzled KV page.
+// The whole head lives in this thread, so the reduction needs no shuffles.
+// ---------------------------------------------------------------------------
+struct QkvRowMeta {
+  int pos, r;
+  size_t page;
+};
+
+SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const QkvRowMeta& rm,
+                                 bool row_ok, int row, int head, __nv_bfloat16* __restrict__ qkv_out,
+                                 int ldd) {
+  // 128 fp32 accumulators -> 64 packed bf16x2 (this is the rounding of the linear output)
+  uint32_t pk[64];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32(tmem_head + half * 64, v0);
+    tmem_ld_32x32(tmem_head + half * 64 + 32, v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      pk[half * 32 + i] = pack_bf16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+      pk[half * 32 + 16 + i] =
+          pack_bf16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+    }
+  }
+  if (!row_ok) return;
+  const bool is_q = head < ea.hq;
+  const bool is_k = !is_q && head < ea.hq + ea.hkv;
+  const __nv_bfloat16* nw =
+      static_cast<const __nv_bfloat16*>(is_q ? ea.q_norm_w : (is_k ? ea.k_norm_w : nullptr));
+  float rstd = 1.f;
+  if (nw != nullptr) {
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      const float2 f = unpack_bf16x2(pk[i]);
+      ss += f.x * f.x + f.y * f.y;
+    }
+    rstd = rsqrtf(ss / static_cast<float>(kHeadDim) + ea.eps);
+  }
+  __nv_bfloat16* dst_lo;
+  int swz = 0;
+  if (is_q) {
+    dst_lo = qkv_out + static_cast<size_t>(row) * ldd + head * kHeadDim;
+  } else {
+    const int kvh = is_k ? (head - ea.hq) : (head - ea.hq - ea.hkv);
+    dst_lo = static_cast<__nv_bfloat16*>(ea.kv_layer) +
+             (rm.page * ea.hkv + kvh) * (2 * kTileElems) + (is_k ? 0 : kTileElems) +
+             rm.r * kHeadDim;
+    swz = rm.r & 7;
+  }
+  const uint4* cosr = reinterpret_cast<const uint4*>(
+      static_cast<const __nv_bfloat16*>(ea.cos_tab) + static_cast<size_t>(rm.pos) * 64);
+  const uint4* sinr = reinterpret_cast<const uint4*>(
+      static_cast<const __nv_bfloat16*>(ea.sin_tab) + static_cast<size_t>(rm.pos) * 64);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {  // dims 8g..8g+7 of the low half and their +64 partners
+    float lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16x2(pk[4 * g + j]);
+      const float2 b = unpack_bf16x2(pk[32 + 4 * g + j]);
+      lo[2 * j] = a.x, lo[2 * j + 1] = a.y;
+      hi[2 * j] = b.x, hi[2 * j + 1] = b.y;
+    }
+    if (nw != nullptr) {
+      const uint4 wl4 = *reinterpret_cast<const uint4*>(nw + 8 * g);
+      const uint4 wh4 = *reinterpret_cast<const uint4*>(nw + 64 + 8 * g);
+      const uint32_t wl[4] = {wl4.x, wl4.y, wl4.z, wl4.w};
+      const uint32_t wh[4] = {wh4.x, wh4.y, wh4.z, wh4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(wl[j]), b = unpack_bf16x2(wh[j]);
+        lo[2 * j] = bf16_round(a.x * bf16_round(lo[2 * j] * rstd));
+        lo[2 * j + 1] = bf16_round(a.y * bf16_round(lo[2 * j + 1] * rstd));
+        hi[2 * j] = bf16_round(b.x * bf16_round(hi[2 * j] * rstd));
+        hi[2 * j + 1] = bf16_round(b.y * bf16_round(hi[2 * j + 1] * rstd));
+      }
+    }
+    if (is_q || is_k) {
+      const uint4 c4 = cosr[g], s4 = sinr[g];
+      const uint32_t cu[4] = {c4.x, c4.y, c4.z, c4.w};
+      const uint32_t su[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 c = unpack_bf16x2(cu[j]), sn = unpack_bf16x2(su[j]);
+        const float cc[2] = {c.x, c.y}, sv[2] = {sn.x, sn.y};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float x = lo[2 * j + e], y = hi[2 * j + e];
+          lo[2 * j + e] = bf16_round(x * cc[e]) + bf16_round(-y * sv[e]);
+          hi[2 * j + e] = bf16_round(y * cc[e]) + bf16_round(x * sv[e]);
+        }
+      }
+    }
+    const uint4 olo = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]),
+                                 pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+    const uint4 ohi = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]),
+                                 pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+    st_v4(dst_lo + ((g ^ swz) << 3), olo);
+    st_v4(dst_lo + (((g + 8) ^ swz) << 3), ohi);
+  }
+}
+
+SB_DEVICE QkvRowMeta qkv_row_meta(const QkvEpiArgs& ea, int row, bool row_ok) {
+  QkvRowMeta rm{0, 0, 0};
+  if (row_ok) {
+    rm.pos = ea.tok_pos[row];
+    const int slot = ea.tok_slot[row];
+    rm.page = static_cast<size_t>(
+        ea.page_table[static_cast<size_t>(slot) * ea.max_pages + rm.pos / kPageTokens]);
+    rm.r = rm.pos % kPageTokens;
+  }
+  return rm;
+}
+
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
                     const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
-                    const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd) {
+                    const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd,
+                    const QkvEpiArgs ea) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -241,15 +363,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       tc_fence_after();
       const int row = m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < M;
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        static_assert(BLOCK_N % 128 == 0 || EPI != EPI_QKV_ROPE, "fused QKV needs whole heads");
+        const QkvRowMeta rm = qkv_row_meta(ea, row, row_ok);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + acc * BLOCK_N + c * 32 + (static_cast<uint32_t>(q * 32) << 16),
-                      v);
-        tmem_ld_wait();
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (!row_ok || col0 >= N) continue;
-        epilogue_store<EPI>(v, d_out, resid, row, col0, ldd);
+        for (int hh = 0; hh < BLOCK_N / 128; ++hh) {
+          const int head = (n_blk * BLOCK_N) / kHeadDim + hh;
+          qkv_head_epilogue(
+              tmem_base + acc * BLOCK_N + hh * 128 + (static_cast<uint32_t>(q * 32) << 16), ea, rm,
+              row_ok && head * kHeadDim < N, row, head, reinterpret_cast<__nv_bfloat16*>(d_out),
+              ldd);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(
+              tmem_base + acc * BLOCK_N + c * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+          tmem_ld_wait();
+          const int col0 = n_blk * BLOCK_N + c * 32;
+          if (!row_ok || col0 >= N) continue;
+          epilogue_store<EPI>(v, d_out, resid, row, col0, ldd);
+        }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -289,7 +424,8 @@ template <int EPI, int k2Stages>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
                      const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
-                     const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd) {
+                     const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd,
+                     const QkvEpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
   // both CTAs of the pair must compute the same offsets: the dynamic smem base is the
   // same in every CTA of a kernel, so the alignment fix-up below is identical too.
@@ -410,15 +546,27 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       tc_fence_after();
       const int row = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
       const bool row_ok = row < M;
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        const QkvRowMeta rm = qkv_row_meta(ea, row, row_ok);
 #pragma unroll 1
-      for (int c = 0; c < k2BlockN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + acc * k2BlockN + c * 32 + (static_cast<uint32_t>(q * 32) << 16),
-                      v);
-        tmem_ld_wait();
-        const int col0 = n_blk * k2BlockN + c * 32;
-        if (!row_ok || col0 >= N) continue;
-        epilogue_store<EPI>(v, d_out, resid, row, col0, ldd);
+        for (int hh = 0; hh < k2BlockN / 128; ++hh) {
+          const int head = (n_blk * k2BlockN) / kHeadDim + hh;
+          qkv_head_epilogue(
+              tmem_base + acc * k2BlockN + hh * 128 + (static_cast<uint32_t>(q * 32) << 16), ea,
+              rm, row_ok && head * kHeadDim < N, row, head,
+              reinterpret_cast<__nv_bfloat16*>(d_out), ldd);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < k2BlockN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(
+              tmem_base + acc * k2BlockN + c * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+          tmem_ld_wait();
+          const int col0 = n_blk * k2BlockN + c * 32;
+          if (!row_ok || col0 >= N) continue;
+          epilogue_store<EPI>(v, d_out, resid, row, col0, ldd);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -524,7 +672,7 @@ int num_sms() {
 
 template <int BLOCK_N, int EPI>
 int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* resid, int M, int N,
-               int K, int ldd, cudaStream_t stream) {
+               int K, int ldd, cudaStream_t stream, const QkvEpiArgs& ea) {
   using Cfg = GemmCfg<BLOCK_N>;
   CUtensorMap tm_a, tm_b;
   if (make_tmap(a, a_rows, K, kBlockM, &tm_a)) return -1;
@@ -539,14 +687,14 @@ int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* re
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(
-      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd);
+      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd, ea);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 template <int EPI, int STAGES>
 int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* resid, int M, int N,
-                int K, int ldd, cudaStream_t stream) {
+                int K, int ldd, cudaStream_t stream, const QkvEpiArgs& ea) {
   CUtensorMap tm_a, tm_b;
   if (make_tmap(a, a_rows, K, 128, &tm_a)) return -1;
   if (make_tmap(w, N, K, 128, &tm_b)) return -1;
@@ -560,27 +708,32 @@ int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* r
   const int tiles = ((M + 255) / 256) * ((N + k2BlockN - 1) / k2BlockN);
   const int clusters = std::min(tiles, num_sms() / 2);
   kern<<<2 * clusters, kGemmThreads, k2SmemBytes(STAGES), stream>>>(
-      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd);
+      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd, ea);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 template <int EPI>
 int launch_epi(int block_n, const void* a, int a_rows, const void* w, void* d, const void* resid,
-               int M, int N, int K, int ldd, cudaStream_t stream) {
+               int M, int N, int K, int ldd, cudaStream_t stream, const QkvEpiArgs& ea) {
   switch (block_n) {
     case 512:  // CTA-pair kernel: 256x256 tile per 2-CTA cluster
-      return launch_cta2<EPI, 7>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_cta2<EPI, 7>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     case 516:  // experiment knobs (tools/gemm_bench.py): same kernel, shallower rings
-      return launch_cta2<EPI, 6>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_cta2<EPI, 6>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     case 514:
-      return launch_cta2<EPI, 4>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_cta2<EPI, 4>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     case 64:
-      return launch_cfg<64, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        set_last_error("gemm_bf16_tn: the fused QKV epilogue needs block_n >= 128");
+        return -1;
+      } else {
+        return launch_cfg<64, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
+      }
     case 128:
-      return launch_cfg<128, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_cfg<128, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     default:
-      return launch_cfg<256, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_cfg<256, EPI>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
   }
 }
 
@@ -612,8 +765,10 @@ int gemm_pick_block_n(int M, int N) {
 }
 
 int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* resid, int M,
-                 int N, int K, int ldd, int epilogue, int block_n, cudaStream_t stream) {
+                 int N, int K, int ldd, int epilogue, int block_n, cudaStream_t stream,
+                 const QkvEpiArgs* qkv_args) {
   if (M <= 0) return 0;
+  const QkvEpiArgs ea = qkv_args ? *qkv_args : QkvEpiArgs{};
   if (K % kBlockK != 0 || N % 32 != 0 || a_rows < M) {
     set_last_error("gemm_bf16_tn: unsupported shape M=%d N=%d K=%d a_rows=%d", M, N, K, a_rows);
     return -1;
@@ -626,17 +781,24 @@ int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* 
   }
   switch (epilogue) {
     case EPI_STORE_BF16:
-      return launch_epi<EPI_STORE_BF16>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_epi<EPI_STORE_BF16>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     case EPI_RESIDUAL_BF16:
       if (!resid) {
         set_last_error("gemm_bf16_tn: residual epilogue without residual pointer");
         return -1;
       }
-      return launch_epi<EPI_RESIDUAL_BF16>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_epi<EPI_RESIDUAL_BF16>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     case EPI_SWIGLU_BF16:
-      return launch_epi<EPI_SWIGLU_BF16>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_epi<EPI_SWIGLU_BF16>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     case EPI_STORE_F32:
-      return launch_epi<EPI_STORE_F32>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream);
+      return launch_epi<EPI_STORE_F32>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
+    case EPI_QKV_ROPE:
+      if (!qkv_args || N % kHeadDim != 0 || N != (ea.hq + 2 * ea.hkv) * kHeadDim) {
+        set_last_error("gemm_bf16_tn: fused QKV epilogue needs its operands and N = heads*128");
+        return -1;
+      }
+      if (block_n == 64) block_n = 128;
+      return launch_epi<EPI_QKV_ROPE>(block_n, a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     default:
       set_last_error("gemm_bf16_tn: unknown epilogue %d", epilogue);
       return -1;

@@ -28,11 +28,29 @@ enum GemmEpilogue {
   EPI_RESIDUAL_BF16 = 1,
   EPI_SWIGLU_BF16 = 2,
   EPI_STORE_F32 = 3,
+  EPI_QKV_ROPE = 4,  // QKV projection fused with q/k-norm + RoPE + paged K/V write (K1+K5)
+};
+
+// Extra operands of EPI_QKV_ROPE: everything rope_kv_write needs, applied to the
+// accumulators in the GEMM epilogue so the [T, qkv_dim] tensor never round-trips HBM.
+struct QkvEpiArgs {
+  const int32_t* tok_pos;
+  const int32_t* tok_slot;
+  const int32_t* page_table;
+  int max_pages;
+  void* kv_layer;
+  const void* cos_tab;
+  const void* sin_tab;
+  const void* q_norm_w;  // nullptr: no per-head norm
+  const void* k_norm_w;
+  int hq, hkv;
+  float eps;
 };
 
 // K1 — D = A · W^T (+ fused epilogue); A:[a_rows>=M, K] bf16, W:[N,K] bf16.
 int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* resid, int M,
-                 int N, int K, int ldd, int epilogue, int block_n, cudaStream_t stream);
+                 int N, int K, int ldd, int epilogue, int block_n, cudaStream_t stream,
+                 const QkvEpiArgs* qkv_args = nullptr);
 int gemm_pick_block_n(int M, int N);
 
 // K4 — RMSNorm over rows: out = bf16(w * bf16(x * rsqrt(mean(x^2) + eps))).

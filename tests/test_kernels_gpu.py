@@ -247,6 +247,48 @@ def test_rope_kv_write(qk_norm):
         assert torch.equal(logical[page, :, 1, r], v[t])
 
 
+@pytest.mark.parametrize("block_n", [128, 256, 512, 0])
+@pytest.mark.parametrize("qk_norm", [True, False])
+def test_gemm_qkv_rope_fused_matches_unfused(qk_norm, block_n):
+    """K1+K5 fused epilogue == plain QKV GEMM followed by rope_kv_write (same rounding
+    points; only the order of the per-head sum of squares differs)."""
+    torch.manual_seed(5)
+    hq, hkv, T, K = 6, 2, 333, 320
+    N = (hq + 2 * hkv) * KV.HD
+    n_slots, max_pages, num_pages = 4, 12, 60
+    a = bf(torch.randn(T, K, device=DEV))
+    w = bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
+    qn = bf(torch.rand(KV.HD, device=DEV) + 0.5) if qk_norm else None
+    kn = bf(torch.rand(KV.HD, device=DEV) + 0.5) if qk_norm else None
+    cos, sin = rope_tables(256)
+    tok_slot = torch.arange(T, dtype=torch.int32) % n_slots
+    tok_pos = (torch.arange(T, dtype=torch.int32) // n_slots) + 5
+    pt = torch.randperm(num_pages)[: n_slots * max_pages].view(n_slots, max_pages).to(torch.int32)
+    d_slot, d_pos, d_pt = tok_slot.to(DEV), tok_pos.to(DEV), pt.to(DEV)
+    # unfused path
+    qkv_a = torch.zeros(T, N, dtype=torch.bfloat16, device=DEV)
+    pool_a = torch.zeros(num_pages, hkv, 2, KV.PAGE, KV.HD, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().sb200_gemm_bf16_tn(L.ptr(a), T, L.ptr(w), L.ptr(qkv_a), 0, T, N, K, N, 0, 0,
+                                       stream()))
+    L.check(L.lib().sb200_rope_kv_write(L.ptr(qkv_a), L.ptr(qn), L.ptr(kn), L.ptr(cos), L.ptr(sin),
+                                        L.ptr(d_slot), L.ptr(d_pos), L.ptr(d_pt), max_pages,
+                                        L.ptr(pool_a), T, hq, hkv, 1e-6, stream()))
+    # fused path
+    qkv_b = torch.zeros(T, N, dtype=torch.bfloat16, device=DEV)
+    pool_b = torch.zeros_like(pool_a)
+    L.check(L.lib().sb200_gemm_qkv_rope(L.ptr(a), T, L.ptr(w), L.ptr(qkv_b), T, K, block_n,
+                                        L.ptr(qn), L.ptr(kn), L.ptr(cos), L.ptr(sin),
+                                        L.ptr(d_slot), L.ptr(d_pos), L.ptr(d_pt), max_pages,
+                                        L.ptr(pool_b), hq, hkv, 1e-6, stream()))
+    torch.cuda.synchronize()
+    qa, qb = qkv_a[:, :hq * KV.HD].float(), qkv_b[:, :hq * KV.HD].float()
+    assert torch.allclose(qa, qb, rtol=2e-2, atol=2e-2)
+    assert (qa != qb).float().mean().item() < 0.01
+    assert torch.allclose(pool_a.float(), pool_b.float(), rtol=2e-2, atol=2e-2)
+    assert (pool_a != pool_b).float().mean().item() < 0.01
+    assert torch.equal(pool_a[:, :, 1], pool_b[:, :, 1])          # V: pure copy, bit-exact
+
+
 # --------------------------------------------------------------------------- attention
 def attn_ref(q, k, v, scale):
     """q: [hq,128], k/v: [L,hkv,128] -> [hq,128]; fp32 softmax, bf16 P (like the kernel)."""
