@@ -130,6 +130,7 @@ SB_DEVICE void epilogue_store(const uint32_t (&v)[32], void* __restrict__ d_out,
 struct QkvRowMeta {
   int pos, r;
   size_t page;
+  uint4 cs[8], sn[8];  // this row's cos/sin (64 bf16 each), fetched while the mainloop runs
 };
 
 SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const QkvRowMeta& rm,
@@ -138,17 +139,13 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
   // 128 fp32 accumulators -> 64 packed bf16x2 (this is the rounding of the linear output)
   uint32_t pk[64];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t v0[32], v1[32];
-    tmem_ld_32x32(tmem_head + half * 64, v0);
-    tmem_ld_32x32(tmem_head + half * 64 + 32, v1);
+  for (int c = 0; c < 4; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_head + c * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      pk[half * 32 + i] = pack_bf16x2(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
-      pk[half * 32 + 16 + i] =
-          pack_bf16x2(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
-    }
+    for (int i = 0; i < 16; ++i)
+      pk[c * 16 + i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
   }
   if (!row_ok) return;
   const bool is_q = head < ea.hq;
@@ -176,10 +173,6 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
              rm.r * kHeadDim;
     swz = rm.r & 7;
   }
-  const uint4* cosr = reinterpret_cast<const uint4*>(
-      static_cast<const __nv_bfloat16*>(ea.cos_tab) + static_cast<size_t>(rm.pos) * 64);
-  const uint4* sinr = reinterpret_cast<const uint4*>(
-      static_cast<const __nv_bfloat16*>(ea.sin_tab) + static_cast<size_t>(rm.pos) * 64);
 #pragma unroll
   for (int g = 0; g < 8; ++g) {  // dims 8g..8g+7 of the low half and their +64 partners
     float lo[8], hi[8];
@@ -205,7 +198,7 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
       }
     }
     if (is_q || is_k) {
-      const uint4 c4 = cosr[g], s4 = sinr[g];
+      const uint4 c4 = rm.cs[g], s4 = rm.sn[g];
       const uint32_t cu[4] = {c4.x, c4.y, c4.z, c4.w};
       const uint32_t su[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
@@ -229,8 +222,8 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
   }
 }
 
-SB_DEVICE QkvRowMeta qkv_row_meta(const QkvEpiArgs& ea, int row, bool row_ok) {
-  QkvRowMeta rm{0, 0, 0};
+SB_DEVICE void qkv_row_meta(const QkvEpiArgs& ea, int row, bool row_ok, QkvRowMeta& rm) {
+  rm.pos = 0, rm.r = 0, rm.page = 0;
   if (row_ok) {
     rm.pos = ea.tok_pos[row];
     const int slot = ea.tok_slot[row];
@@ -238,7 +231,15 @@ SB_DEVICE QkvRowMeta qkv_row_meta(const QkvEpiArgs& ea, int row, bool row_ok) {
         ea.page_table[static_cast<size_t>(slot) * ea.max_pages + rm.pos / kPageTokens]);
     rm.r = rm.pos % kPageTokens;
   }
-  return rm;
+  const uint4* cosr = reinterpret_cast<const uint4*>(
+      static_cast<const __nv_bfloat16*>(ea.cos_tab) + static_cast<size_t>(rm.pos) * 64);
+  const uint4* sinr = reinterpret_cast<const uint4*>(
+      static_cast<const __nv_bfloat16*>(ea.sin_tab) + static_cast<size_t>(rm.pos) * 64);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    rm.cs[g] = cosr[g];
+    rm.sn[g] = sinr[g];
+  }
 }
 
 template <int BLOCK_N, int EPI>
@@ -359,13 +360,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_to_mn<16>(tile, num_m, num_n, m_blk, n_blk);
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-      tc_fence_after();
       const int row = m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < M;
+      QkvRowMeta rm;
+      if constexpr (EPI == EPI_QKV_ROPE) qkv_row_meta(ea, row, row_ok, rm);  // overlaps the mainloop
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
       if constexpr (EPI == EPI_QKV_ROPE) {
         static_assert(BLOCK_N % 128 == 0 || EPI != EPI_QKV_ROPE, "fused QKV needs whole heads");
-        const QkvRowMeta rm = qkv_row_meta(ea, row, row_ok);
 #pragma unroll 1
         for (int hh = 0; hh < BLOCK_N / 128; ++hh) {
           const int head = (n_blk * BLOCK_N) / kHeadDim + hh;
@@ -542,12 +544,13 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int m_blk, n_blk;
       tile_to_mn<8>(tile, num_m, num_n, m_blk, n_blk);
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-      tc_fence_after();
       const int row = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
       const bool row_ok = row < M;
+      QkvRowMeta rm;
+      if constexpr (EPI == EPI_QKV_ROPE) qkv_row_meta(ea, row, row_ok, rm);  // overlaps the mainloop
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
       if constexpr (EPI == EPI_QKV_ROPE) {
-        const QkvRowMeta rm = qkv_row_meta(ea, row, row_ok);
 #pragma unroll 1
         for (int hh = 0; hh < k2BlockN / 128; ++hh) {
           const int head = (n_blk * k2BlockN) / kHeadDim + hh;
