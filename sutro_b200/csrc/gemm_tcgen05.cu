@@ -55,8 +55,7 @@ struct GemmCfg {
 // before moving on, so the CTAs running concurrently share a [GM*128, K] slab of A and a
 // ~148/GM-tile slab of W that both fit in the 126 MB L2.  (M-fastest order re-read A from
 // HBM once per N tile: 5x the algorithmic traffic on the down projection, ncu r01.)
-template <int GM>
-SB_DEVICE void tile_to_mn(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+SB_DEVICE void tile_to_mn(int GM, int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
   const int group_tiles = GM * num_n;
   const int g = tile / group_tiles;
   const int first_m = g * GM;
@@ -247,7 +246,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
                     const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
                     const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd,
-                    const QkvEpiArgs ea) {
+                    int ea_gm, const QkvEpiArgs ea) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -299,7 +298,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
-        tile_to_mn<16>(tile, num_m, num_n, m_blk, n_blk);
+        tile_to_mn(ea_gm, tile, num_m, num_n, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -359,7 +358,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
-      tile_to_mn<16>(tile, num_m, num_n, m_blk, n_blk);
+      tile_to_mn(ea_gm, tile, num_m, num_n, m_blk, n_blk);
       const int row = m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < M;
       QkvRowMeta rm;
@@ -427,7 +426,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
                      const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
                      const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd,
-                     const QkvEpiArgs ea) {
+                     int ea_gm, const QkvEpiArgs ea) {
   extern __shared__ uint8_t smem_raw[];
   // both CTAs of the pair must compute the same offsets: the dynamic smem base is the
   // same in every CTA of a kernel, so the alignment fix-up below is identical too.
@@ -483,7 +482,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int m_blk, n_blk;
-        tile_to_mn<8>(tile, num_m, num_n, m_blk, n_blk);
+        tile_to_mn(ea_gm, tile, num_m, num_n, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb_leader = smem_u32(&full_bar[stage]) & kPeerBitMask;
@@ -543,7 +542,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       int m_blk, n_blk;
-      tile_to_mn<8>(tile, num_m, num_n, m_blk, n_blk);
+      tile_to_mn(ea_gm, tile, num_m, num_n, m_blk, n_blk);
       const int row = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
       const bool row_ok = row < M;
       QkvRowMeta rm;
@@ -673,6 +672,16 @@ int num_sms() {
   return n;
 }
 
+// Row-tiles per raster group: as many as keep the group's A slab (rows x K bf16) within
+// ~48 MB of the 126 MB L2, so A is read from HBM once and W once per group.
+int raster_group(int tile_rows, int K) {
+  const long slab = 48L << 20;
+  long gm = slab / (static_cast<long>(tile_rows) * K * 2);
+  if (gm < 2) gm = 2;
+  if (gm > 64) gm = 64;
+  return static_cast<int>(gm);
+}
+
 template <int BLOCK_N, int EPI>
 int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* resid, int M, int N,
                int K, int ldd, cudaStream_t stream, const QkvEpiArgs& ea) {
@@ -690,7 +699,8 @@ int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* re
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(
-      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd, ea);
+      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd,
+      raster_group(kBlockM, K), ea);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -711,7 +721,8 @@ int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* r
   const int tiles = ((M + 255) / 256) * ((N + k2BlockN - 1) / k2BlockN);
   const int clusters = std::min(tiles, num_sms() / 2);
   kern<<<2 * clusters, kGemmThreads, k2SmemBytes(STAGES), stream>>>(
-      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd, ea);
+      tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd,
+      raster_group(256, K), ea);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
