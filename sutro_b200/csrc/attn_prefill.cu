@@ -7,9 +7,10 @@
 // Work decomposition: CTA = (q tile, kv head) of one sequence.  The CTA has 8
 // warps = G query heads x (QT/16) token sub-tiles, QT = 128/G, so all heads of
 // a GQA group reuse each K/V page loaded into shared memory.  Pages stream
-// through a 4-stage cp.async.bulk ring (flat 8 KiB copies of pre-swizzled
-// tiles, see kernels.h); math is FlashAttention-2 style on mma.sync m16n8k16
-// with fp32 online softmax.
+// through a 3-stage cp.async.bulk ring of 32-token super-tiles (two flat 8 KiB
+// copies of pre-swizzled tiles per stage, see kernels.h) so that one barrier
+// round and one softmax rescale cover 32 KV tokens; math is FlashAttention-2
+// style on mma.sync m16n8k16 with fp32 online softmax.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -18,8 +19,8 @@ namespace sb {
 namespace {
 
 constexpr int kPfWarps = 8;
-constexpr int kPfStages = 4;
-constexpr int kPfStageBytes = 2 * kTileBytes;
+constexpr int kPfStages = 3;                    // ring of 32-token super-tiles (2 pages)
+constexpr int kPfStageBytes = 4 * kTileBytes;   // K0 | V0 | K1 | V1
 constexpr int kPfSmem = kPfStages * kPfStageBytes + 1024;
 
 template <int G>
@@ -52,7 +53,8 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   const int q0 = qt0 + sub * 16;              // first query token (within the sequence's new tokens)
   const int cta_q_end = min(qt0 + QT, q_len);  // exclusive
   const int last_kv_pos = past + cta_q_end - 1;
-  const int n_tiles = last_kv_pos / kPageTokens + 1;
+  const int n_pages = last_kv_pos / kPageTokens + 1;
+  const int n_super = (n_pages + 1) >> 1;      // 32-token super-tiles
   const int warp_last_pos = past + min(q0 + 16, q_len) - 1;  // causal horizon of this warp
   const bool warp_active = q0 < q_len;
 
@@ -63,18 +65,24 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   }
   __syncthreads();
 
-  auto issue = [&](int tile, int stage) {
-    const int page = pt[tile];
-    const __nv_bfloat16* src =
-        kv_layer + (static_cast<size_t>(page) * hkv + kvh) * (2 * kTileElems);
+  // one super-tile = up to two pages, each one flat 8 KiB copy (K tile + V tile)
+  auto issue = [&](int sup, int stage) {
+    const int p0 = 2 * sup;
+    const bool two = p0 + 1 < n_pages;
     const uint32_t bar = smem_u32(&full_bar[stage]);
-    mbar_arrive_expect_tx(bar, kPfStageBytes);
-    bulk_load_1d(smem_u32(smem + stage * kPfStageBytes), src, kPfStageBytes, bar);
+    const uint32_t dst = smem_u32(smem + stage * kPfStageBytes);
+    mbar_arrive_expect_tx(bar, two ? 4 * kTileBytes : 2 * kTileBytes);
+    bulk_load_1d(dst, kv_layer + (static_cast<size_t>(pt[p0]) * hkv + kvh) * (2 * kTileElems),
+                 2 * kTileBytes, bar);
+    if (two)
+      bulk_load_1d(dst + 2 * kTileBytes,
+                   kv_layer + (static_cast<size_t>(pt[p0 + 1]) * hkv + kvh) * (2 * kTileElems),
+                   2 * kTileBytes, bar);
   };
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kPfStages - 1; ++s)
-      if (s < n_tiles) issue(s, s);
+      if (s < n_super) issue(s, s);
   }
 
   // Q fragments for this warp's 16 tokens x 128 dims.
@@ -106,73 +114,86 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   const int lm = lane >> 3;
   const int lr = lane & 7;
 
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    const int stage = tile % kPfStages;
-    const uint32_t phase = (tile / kPfStages) & 1;
+  for (int sup = 0; sup < n_super; ++sup) {
+    const int stage = sup % kPfStages;
+    const uint32_t phase = (sup / kPfStages) & 1;
     // keep the ring full: the stage freed by the previous iteration's barrier
     if (threadIdx.x == 0) {
-      const int nxt = tile + kPfStages - 1;
-      if (nxt < n_tiles) {
+      const int nxt = sup + kPfStages - 1;
+      if (nxt < n_super) {
         fence_proxy_async_smem();
         issue(nxt, nxt % kPfStages);
       }
     }
     mbar_wait(smem_u32(&full_bar[stage]), phase);
 
-    if (warp_active && tile * kPageTokens <= warp_last_pos) {
-      const uint32_t ks = smem_u32(smem + stage * kPfStageBytes);
-      const uint32_t vs = ks + kTileBytes;
-      float s0[4] = {0.f, 0.f, 0.f, 0.f};
-      float s1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (warp_active && sup * 32 <= warp_last_pos) {
+      const uint32_t base = smem_u32(smem + stage * kPfStageBytes);
+      // second page of the super-tile: absent at an odd tail, or wholly above this warp's
+      // causal horizon (then it is skipped: its shared memory may hold stale bytes)
+      const bool two = (2 * sup + 1 < n_pages) && (sup * 32 + 16 <= warp_last_pos);
+      float s[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
         const int tok = (lm >> 1) * 8 + lr;
         const int chunk = kk * 2 + (lm & 1);
+        const uint32_t off = tok * 256 + ((chunk ^ (tok & 7)) << 4);
         uint32_t b0, b1, b2, b3;
-        ldmatrix_x4(ks + tok * 256 + ((chunk ^ (tok & 7)) << 4), b0, b1, b2, b3);
-        mma_bf16_16816(s0, qa[kk], b0, b1);
-        mma_bf16_16816(s1, qa[kk], b2, b3);
+        ldmatrix_x4(base + off, b0, b1, b2, b3);
+        mma_bf16_16816(s[0], qa[kk], b0, b1);
+        mma_bf16_16816(s[1], qa[kk], b2, b3);
+        if (two) {
+          ldmatrix_x4(base + 2 * kTileBytes + off, b0, b1, b2, b3);
+          mma_bf16_16816(s[2], qa[kk], b0, b1);
+          mma_bf16_16816(s[3], qa[kk], b2, b3);
+        }
       }
-      // causal mask: kv position > query position
-      const int kp = tile * kPageTokens + 2 * (lane & 3);
-      float sv[2][4] = {{s0[0], s0[1], s1[0], s1[1]}, {s0[2], s0[3], s1[2], s1[3]}};
+      // causal mask (kv position > query position); a skipped second page counts as masked
+      const int kp = sup * 32 + 2 * (lane & 3);
+      float alpha[2];
+      uint32_t pa[2][4];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int qp = pos_r0 + 8 * h;
-        if (kp > qp) sv[h][0] = -INFINITY;
-        if (kp + 1 > qp) sv[h][1] = -INFINITY;
-        if (kp + 8 > qp) sv[h][2] = -INFINITY;
-        if (kp + 9 > qp) sv[h][3] = -INFINITY;
-      }
-      float alpha[2];
-      uint32_t pa[4];
+        float sv[8];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float mx = fmaxf(fmaxf(sv[h][0], sv[h][1]), fmaxf(sv[h][2], sv[h][3]));
+        for (int nt = 0; nt < 4; ++nt) {
+          const int k0 = kp + 8 * nt;
+          const bool dead = (nt >= 2) && !two;
+          sv[2 * nt] = (dead || k0 > qp) ? -INFINITY : s[nt][2 * h];
+          sv[2 * nt + 1] = (dead || k0 + 1 > qp) ? -INFINITY : s[nt][2 * h + 1];
+        }
+        float mx = sv[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, sv[i]);
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         const float m_new = fmaxf(m_run[h], mx);
-        // a row can be fully masked in this tile only if an earlier tile already
-        // gave it a finite max (position 0 is always visible), except for padding rows
+        // only padding rows can be fully masked here (position 0 is visible to every real row)
         const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
         alpha[h] = exp2f((m_run[h] - m_use) * scale_log2);
-        float p[4];
+        float p[8], ps = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) p[i] = exp2f((sv[h][i] - m_use) * scale_log2);
-        float ps = p[0] + p[1] + p[2] + p[3];
+        for (int i = 0; i < 8; ++i) {
+          p[i] = exp2f((sv[i] - m_use) * scale_log2);
+          ps += p[i];
+        }
         ps += __shfl_xor_sync(0xffffffffu, ps, 1);
         ps += __shfl_xor_sync(0xffffffffu, ps, 2);
         l_run[h] = l_run[h] * alpha[h] + ps;
         m_run[h] = m_new;
-        pa[h] = pack_bf16x2(p[0], p[1]);
-        pa[2 + h] = pack_bf16x2(p[2], p[3]);
+        pa[0][h] = pack_bf16x2(p[0], p[1]);
+        pa[0][2 + h] = pack_bf16x2(p[2], p[3]);
+        pa[1][h] = pack_bf16x2(p[4], p[5]);
+        pa[1][2 + h] = pack_bf16x2(p[6], p[7]);
       }
 #pragma unroll
       for (int nt = 0; nt < 16; nt += 2) {
         const int tok = (lm & 1) * 8 + lr;
         const int chunk = nt + (lm >> 1);
-        uint32_t b0, b1, b2, b3;
-        ldmatrix_x4_trans(vs + tok * 256 + ((chunk ^ (tok & 7)) << 4), b0, b1, b2, b3);
+        const uint32_t off = kTileBytes + tok * 256 + ((chunk ^ (tok & 7)) << 4);
         o[nt][0] *= alpha[0];
         o[nt][1] *= alpha[0];
         o[nt][2] *= alpha[1];
@@ -181,8 +202,15 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         o[nt + 1][1] *= alpha[0];
         o[nt + 1][2] *= alpha[1];
         o[nt + 1][3] *= alpha[1];
-        mma_bf16_16816(o[nt], pa, b0, b1);
-        mma_bf16_16816(o[nt + 1], pa, b2, b3);
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(base + off, b0, b1, b2, b3);
+        mma_bf16_16816(o[nt], pa[0], b0, b1);
+        mma_bf16_16816(o[nt + 1], pa[0], b2, b3);
+        if (two) {
+          ldmatrix_x4_trans(base + 2 * kTileBytes + off, b0, b1, b2, b3);
+          mma_bf16_16816(o[nt], pa[1], b0, b1);
+          mma_bf16_16816(o[nt + 1], pa[1], b2, b3);
+        }
       }
     }
     __syncthreads();  // everyone is done with this stage -> it may be refilled
