@@ -37,8 +37,14 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kAccStages = 2;
-constexpr int kGemmThreads = 256;
 constexpr int kEpiWarp0 = 4;
+// 4 epilogue warps (one per TMEM lane quarter); the fused QKV epilogue does an order of
+// magnitude more math per element, so it gets two warps per quarter, each owning half of
+// every head (dims [32p,32p+32) and their +64 RoPE partners).
+template <int EPI>
+constexpr int epi_warps() { return EPI == EPI_QKV_ROPE ? 8 : 4; }
+template <int EPI>
+constexpr int gemm_threads() { return 128 + 32 * epi_warps<EPI>(); }
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -129,38 +135,38 @@ SB_DEVICE void epilogue_store(const uint32_t (&v)[32], void* __restrict__ d_out,
 struct QkvRowMeta {
   int pos, r;
   size_t page;
-  uint4 cs[8], sn[8];  // this row's cos/sin (64 bf16 each), fetched while the mainloop runs
+  uint4 cs[4], sn[4];  // this row's cos/sin for the warp's 32 dims, fetched during the mainloop
 };
 
 SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const QkvRowMeta& rm,
                                  bool row_ok, int row, int head, __nv_bfloat16* __restrict__ qkv_out,
-                                 int ldd) {
+                                 int ldd, int part) {
   // 128 fp32 accumulators -> 64 packed bf16x2 (this is the rounding of the linear output)
-  uint32_t pk[64];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t v[32];
-    tmem_ld_32x32(tmem_head + c * 32, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      pk[c * 16 + i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-  }
-  if (!row_ok) return;
+  // This warp owns dims [32*part, 32*part+32) and [64+32*part, ...): TMEM column chunks
+  // `part` and `part+2`.  The other two chunks are read only for the sum of squares.
   const bool is_q = head < ea.hq;
   const bool is_k = !is_q && head < ea.hq + ea.hkv;
   const __nv_bfloat16* nw =
       static_cast<const __nv_bfloat16*>(is_q ? ea.q_norm_w : (is_k ? ea.k_norm_w : nullptr));
-  float rstd = 1.f;
-  if (nw != nullptr) {
-    float ss = 0.f;
+  uint32_t pk[32];  // [0,16): low-half dims, [16,32): their +64 partners (bf16x2 packed)
+  float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) {
-      const float2 f = unpack_bf16x2(pk[i]);
+  for (int c = 0; c < 4; ++c) {
+    const bool mine = (c & 1) == part;
+    if (!mine && nw == nullptr) continue;  // warp-uniform: nothing needed from this chunk
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_head + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t u = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      const float2 f = unpack_bf16x2(u);  // the bf16-rounded projection output
       ss += f.x * f.x + f.y * f.y;
+      if (mine) pk[(c >> 1) * 16 + i] = u;
     }
-    rstd = rsqrtf(ss / static_cast<float>(kHeadDim) + ea.eps);
   }
+  if (!row_ok) return;
+  const float rstd = nw != nullptr ? rsqrtf(ss / static_cast<float>(kHeadDim) + ea.eps) : 1.f;
   __nv_bfloat16* dst_lo;
   int swz = 0;
   if (is_q) {
@@ -173,12 +179,13 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
     swz = rm.r & 7;
   }
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {  // dims 8g..8g+7 of the low half and their +64 partners
+  for (int gg = 0; gg < 4; ++gg) {  // dims 8g..8g+7 of the low half and their +64 partners
+    const int g = 4 * part + gg;
     float lo[8], hi[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 a = unpack_bf16x2(pk[4 * g + j]);
-      const float2 b = unpack_bf16x2(pk[32 + 4 * g + j]);
+      const float2 a = unpack_bf16x2(pk[4 * gg + j]);
+      const float2 b = unpack_bf16x2(pk[16 + 4 * gg + j]);
       lo[2 * j] = a.x, lo[2 * j + 1] = a.y;
       hi[2 * j] = b.x, hi[2 * j + 1] = b.y;
     }
@@ -197,7 +204,7 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
       }
     }
     if (is_q || is_k) {
-      const uint4 c4 = rm.cs[g], s4 = rm.sn[g];
+      const uint4 c4 = rm.cs[gg], s4 = rm.sn[gg];
       const uint32_t cu[4] = {c4.x, c4.y, c4.z, c4.w};
       const uint32_t su[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
@@ -221,7 +228,7 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
   }
 }
 
-SB_DEVICE void qkv_row_meta(const QkvEpiArgs& ea, int row, bool row_ok, QkvRowMeta& rm) {
+SB_DEVICE void qkv_row_meta(const QkvEpiArgs& ea, int row, bool row_ok, int part, QkvRowMeta& rm) {
   rm.pos = 0, rm.r = 0, rm.page = 0;
   if (row_ok) {
     rm.pos = ea.tok_pos[row];
@@ -235,14 +242,14 @@ SB_DEVICE void qkv_row_meta(const QkvEpiArgs& ea, int row, bool row_ok, QkvRowMe
   const uint4* sinr = reinterpret_cast<const uint4*>(
       static_cast<const __nv_bfloat16*>(ea.sin_tab) + static_cast<size_t>(rm.pos) * 64);
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    rm.cs[g] = cosr[g];
-    rm.sn[g] = sinr[g];
+  for (int g = 0; g < 4; ++g) {
+    rm.cs[g] = cosr[4 * part + g];
+    rm.sn[g] = sinr[4 * part + g];
   }
 }
 
 template <int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
                     const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
                     const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd,
@@ -273,7 +280,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 128);
+      mbar_init(smem_u32(&tempty_bar[a]), 32 * epi_warps<EPI>());
     }
     fence_mbar_init();
   }
@@ -354,6 +361,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue =====
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int part = (warp - kEpiWarp0) >> 2;  // 0, or 1 for the second warp of a quarter
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -362,7 +370,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       const int row = m_blk * kBlockM + q * 32 + lane;
       const bool row_ok = row < M;
       QkvRowMeta rm;
-      if constexpr (EPI == EPI_QKV_ROPE) qkv_row_meta(ea, row, row_ok, rm);  // overlaps the mainloop
+      if constexpr (EPI == EPI_QKV_ROPE) qkv_row_meta(ea, row, row_ok, part, rm);  // overlaps the mainloop
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       if constexpr (EPI == EPI_QKV_ROPE) {
@@ -373,7 +381,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
           qkv_head_epilogue(
               tmem_base + acc * BLOCK_N + hh * 128 + (static_cast<uint32_t>(q * 32) << 16), ea, rm,
               row_ok && head * kHeadDim < N, row, head, reinterpret_cast<__nv_bfloat16*>(d_out),
-              ldd);
+              ldd, part);
         }
       } else {
 #pragma unroll 1
@@ -422,7 +430,7 @@ constexpr int k2BlockN = 256;
 constexpr int k2SmemBytes(int stages) { return stages * k2StageBytes + 256 + 1024; }
 
 template <int EPI, int k2Stages>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
                      const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
                      const __nv_bfloat16* __restrict__ resid, int M, int N, int K, int ldd,
@@ -455,7 +463,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(smem_u32(&tempty_bar[a]), 2 * epi_warps<EPI>());  // epilogue warps x 2 CTAs
     }
     fence_mbar_init();
   }
@@ -538,6 +546,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue (both CTAs: each drains its own 128 accumulator rows) =====
     const int q = warp & 3;
+    const int part = (warp - kEpiWarp0) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -546,7 +555,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       const int row = m_blk * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
       const bool row_ok = row < M;
       QkvRowMeta rm;
-      if constexpr (EPI == EPI_QKV_ROPE) qkv_row_meta(ea, row, row_ok, rm);  // overlaps the mainloop
+      if constexpr (EPI == EPI_QKV_ROPE) qkv_row_meta(ea, row, row_ok, part, rm);  // overlaps the mainloop
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       if constexpr (EPI == EPI_QKV_ROPE) {
@@ -556,7 +565,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
           qkv_head_epilogue(
               tmem_base + acc * k2BlockN + hh * 128 + (static_cast<uint32_t>(q * 32) << 16), ea,
               rm, row_ok && head * kHeadDim < N, row, head,
-              reinterpret_cast<__nv_bfloat16*>(d_out), ldd);
+              reinterpret_cast<__nv_bfloat16*>(d_out), ldd, part);
         }
       } else {
 #pragma unroll 1
@@ -698,7 +707,7 @@ int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* re
   }
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(
+  kern<<<grid, gemm_threads<EPI>(), Cfg::kSmemBytes, stream>>>(
       tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd,
       raster_group(kBlockM, K), ea);
   SB_CUDA_CHECK(cudaGetLastError());
@@ -720,7 +729,7 @@ int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* r
   }
   const int tiles = ((M + 255) / 256) * ((N + k2BlockN - 1) / k2BlockN);
   const int clusters = std::min(tiles, num_sms() / 2);
-  kern<<<2 * clusters, kGemmThreads, k2SmemBytes(STAGES), stream>>>(
+  kern<<<2 * clusters, gemm_threads<EPI>(), k2SmemBytes(STAGES), stream>>>(
       tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd,
       raster_group(256, K), ea);
   SB_CUDA_CHECK(cudaGetLastError());
