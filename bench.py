@@ -121,6 +121,7 @@ def cpu_baseline(spec, hf_weights, vocab, rows, threads: int, budget_s: float = 
     t_init = time.perf_counter()
     tok, model = RefTokenizer(vocab), RefModel(spec, hf_weights, fast=True)
     fsm = TokenFSM(compile_schema(SCHEMA), vocab)
+    fsm.enable_jump_forward(tok)    # same decoding algorithm as the engine (jump-forward)
     tpl = VB.chat_template(spec.family, SYSTEM_PROMPT)
     log(f"cpu baseline: oracle ready in {time.perf_counter() - t_init:.1f}s, {threads} threads")
     import signal
@@ -217,7 +218,9 @@ def workload_config(args, rows_per_gpu):
             "weights": "seeded random init (no checkpoints offline)",
             "vocab": "seeded synthetic byte-level BPE", "parallelism": f"row-sharded x{args.gpus}",
             "l2": "inputs_exceed_l2 (8 GB of weights + KV streamed per step; L2 is 126 MB)",
-            "max_slots": args.max_slots, "max_prefill_tokens": args.max_prefill_tokens}
+            "max_slots": args.max_slots, "max_prefill_tokens": args.max_prefill_tokens,
+            "decoding": "greedy + schema mask, jump-forward (forced JSON syntax is fed with the "
+                        "prompt / appended, not decoded token by token)"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -387,7 +390,8 @@ def main():
             "cpu_baseline": cpu, "clocks": clk,
             "outputs_valid": bool(ok),
             "job": {k: st[k] for k in ("prefill_steps", "decode_steps", "prefix_cached_tokens",
-                                       "input_tokens", "output_tokens", "fsm_states")},
+                                       "input_tokens", "output_tokens", "decode_tokens",
+                                       "fsm_states", "jump_forward", "forced_prefix_tokens")},
             "phase_s_last_step": {k: st[k] for k in ("t_h2d_s", "t_tokenize_s", "t_engine_s",
                                                      "t_detok_s", "t_d2h_s")},
             "setup_s": setup_s, "weight_broadcast_ms": bcast_ms,

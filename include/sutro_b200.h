@@ -170,7 +170,14 @@ typedef struct {
   const uint8_t* fsm_accept;
   const uint8_t* fsm_final;
   int fsm_states;
-  int fsm_start;
+  int fsm_start;                  /* state after the forced prefix when n_forced_prefix > 0  */
+  /* jump-forward decoding (optional): the last n_forced_prefix tokens of suffix_tokens are
+   * output the automaton forces on every row (fed with the prompt, reported as output);
+   * fsm_tail_off[fsm_states+1] / fsm_tail_tok give, per state, the tokens of a continuation
+   * that is forced all the way to a final state (appended without running the model). */
+  int n_forced_prefix;
+  const int32_t* fsm_tail_off;    /* host, NULL = no tails */
+  const int32_t* fsm_tail_tok;    /* host */
   /* outputs, device, caller-allocated (results["outputs"], sutro/sdk.py:406)           */
   int32_t* out_tokens_dev;        /* [n_rows, max_new_tokens]                           */
   int32_t* out_len_dev;           /* [n_rows]                                           */

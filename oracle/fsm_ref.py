@@ -33,6 +33,8 @@ class TokenFSM:
                 pad[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
         self.pad = pad
         self._cache: Dict[int, torch.Tensor] = {}
+        self.forced_prefix: List[int] = []
+        self.tails: Dict[int, List[int]] = {}
 
     def allowed(self, state: int) -> torch.Tensor:
         if state not in self._cache:
@@ -56,6 +58,35 @@ class TokenFSM:
 
     def is_final(self, state: int) -> bool:
         return state < 0 or bool(self.dfa.final[state])
+
+    # ---- jump-forward decoding (restated independently of sutro_b200.schema_fsm) ----
+    def _forced(self, state: int):
+        out, s = bytearray(), state
+        while not self.dfa.accept[s]:
+            nxt = np.nonzero(self.dfa.trans[s] >= 0)[0]
+            if len(nxt) != 1:
+                break
+            out.append(int(nxt[0]))
+            s = int(self.dfa.trans[s, nxt[0]])
+        return bytes(out), s
+
+    def enable_jump_forward(self, tokenizer) -> bool:
+        """tokenizer: oracle RefTokenizer.  Sets `forced_prefix` (token ids every output starts
+        with), moves `start` past it, and fills `tails[state]` (token ids of a continuation
+        that is forced up to a final state).  Returns False when the whole output is forced
+        (then nothing is enabled, like the engine)."""
+        prefix, after = self._forced(self.dfa.start)
+        tails = {}
+        for s in range(self.dfa.n_states):
+            run, end = self._forced(s)
+            if run and self.dfa.final[end]:
+                tails[s] = run
+        if self.dfa.final[after] or after in tails:
+            return False
+        self.forced_prefix = tokenizer.encode(prefix.decode("utf-8"))
+        self.start = after
+        self.tails = {s: tokenizer.encode(b.decode("utf-8")) for s, b in tails.items()}
+        return True
 
 
 # ---- a deliberately small, independent JSON-Schema validator (subset used by tests) ----

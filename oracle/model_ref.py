@@ -67,10 +67,12 @@ def rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
 @dataclass
 class GenResult:
     tokens: List[int]
-    margins: List[float]        # top1 - top2 logit among allowed tokens, one per decision
-                                # (len(tokens), +1 when the last decision was EOS)
+    margins: List[float]        # top1 - top2 logit among allowed tokens, one per DECISION
+                                # (forced jump-forward tokens are not decisions);
+                                # decision_index[i] = position in `tokens` of decision i
     finished_by: str            # "eos" | "fsm" | "length"
     runner_up: Optional[List[int]] = None   # second-best allowed token at each decision
+    decision_pos: Optional[List[int]] = None  # index into `tokens` of each decision (EOS: len)
 
 
 class RefModel:
@@ -154,10 +156,13 @@ class RefModel:
         """Greedy decode.  `fsm` (oracle/fsm_ref.TokenFSM-like) supplies, per state, a bool
         mask over the vocabulary and the transition on a token."""
         cache = [None] * self.spec.n_layers
+        forced = list(getattr(fsm, "forced_prefix", [])) if fsm is not None else []
+        prompt = list(prompt) + forced          # jump-forward: forced output rides with the prompt
         h = self._forward(prompt, 0, cache)[-1:]
-        out: List[int] = []
+        out: List[int] = list(forced)
         margins: List[float] = []
         second: List[int] = []
+        dpos: List[int] = []
         state = fsm.start if fsm is not None else None
         pos = len(prompt)
         why = "length"
@@ -171,6 +176,7 @@ class RefModel:
             best = top.values[0]
             tok = int((lg == best).nonzero()[0])
             margins.append(float(top.values[0] - top.values[1]))
+            dpos.append(len(out))
             second.append(int(top.indices[1]) if int(top.indices[0]) == tok else int(top.indices[0]))
             if tok == eos_id and not ignore_eos:
                 why = "eos"
@@ -181,8 +187,13 @@ class RefModel:
                 if fsm.is_final(state):
                     why = "fsm"
                     break
+                tail = getattr(fsm, "tails", {}).get(state)
+                if tail:                         # forced all the way to a final state
+                    out += tail[:max(0, max_new - len(out))]
+                    why = "fsm"
+                    break
             if len(out) >= max_new:
                 break
             h = self._forward([tok], pos, cache)
             pos += 1
-        return GenResult(out, margins, why, second)
+        return GenResult(out, margins, why, second, dpos)

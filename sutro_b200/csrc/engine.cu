@@ -63,14 +63,21 @@ __global__ void __launch_bounds__(128)
 init_slots_kernel(const SeqInit* __restrict__ seqs, const int32_t* __restrict__ pt_rows,
                   int max_pages, int32_t* __restrict__ page_table, int32_t* slot_state,
                   int32_t* slot_ngen, int32_t* slot_pos, int32_t* slot_done, int32_t* slot_row,
-                  int32_t* slot_maxnew, int32_t* slot_next_tok) {
+                  int32_t* slot_maxnew, int32_t* slot_next_tok, const int32_t* __restrict__ forced,
+                  int n_forced, int32_t* __restrict__ out_tokens, int32_t* __restrict__ out_len,
+                  int out_stride) {
   const SeqInit s = seqs[blockIdx.x];
   for (int i = threadIdx.x; i < max_pages; i += blockDim.x)
     page_table[static_cast<size_t>(s.slot) * max_pages + i] =
         pt_rows[static_cast<size_t>(blockIdx.x) * max_pages + i];
+  // jump-forward: the forced output prefix was fed with the prompt; it is output too
+  if (s.row >= 0 && out_tokens != nullptr)
+    for (int i = threadIdx.x; i < n_forced; i += blockDim.x)
+      out_tokens[static_cast<size_t>(s.row) * out_stride + i] = forced[i];
   if (threadIdx.x == 0) {
+    if (s.row >= 0 && out_len != nullptr) out_len[s.row] = n_forced;
     slot_state[s.slot] = s.fsm_start;
-    slot_ngen[s.slot] = 0;
+    slot_ngen[s.slot] = s.row >= 0 ? n_forced : 0;
     slot_pos[s.slot] = s.past + s.q_len - 1;  // sampler increments: next position = prompt length
     slot_done[s.slot] = 0;
     slot_row[s.slot] = s.row;
@@ -184,6 +191,7 @@ struct Engine {
   int32_t* d_fsm_trans = nullptr;
   uint8_t *d_fsm_accept = nullptr, *d_fsm_final = nullptr;
   uint32_t* d_mask_bits = nullptr;
+  int32_t *d_tail_off = nullptr, *d_tail_tok = nullptr;  // jump-forward terminal tails
   int mask_words = 0;
   size_t fsm_cap_states = 0;
   // job-scoped prompt pieces
@@ -204,7 +212,8 @@ struct Engine {
                     (void*)slot_next_tok, (void*)slot_pos, (void*)slot_done, (void*)slot_row,
                     (void*)slot_maxnew, (void*)d_stage, (void*)d_tok_bytes, (void*)d_tok_off,
                     (void*)d_fsm_trans, (void*)d_fsm_accept, (void*)d_fsm_final,
-                    (void*)d_mask_bits, (void*)d_prefix, (void*)d_suffix})
+                    (void*)d_mask_bits, (void*)d_prefix, (void*)d_suffix, (void*)d_tail_off,
+                    (void*)d_tail_tok})
       cudaFree(p);
     if (h_stage) cudaFreeHost(h_stage);
     if (h_done) cudaFreeHost(h_done);
@@ -354,6 +363,8 @@ struct Engine {
       a.fsm_trans = d_fsm_trans;
       a.fsm_accept = d_fsm_accept;
       a.fsm_final = d_fsm_final;
+      a.fsm_tail_off = has_fsm ? d_tail_off : nullptr;
+      a.fsm_tail_tok = d_tail_tok;
       a.tok_bytes = d_tok_bytes;
       a.tok_off = d_tok_off;
       a.eos_id = c.eos_id;
@@ -386,6 +397,18 @@ struct Engine {
                                   stream));
     SB_CUDA_CHECK(cudaMemcpyAsync(d_fsm_accept, job.fsm_accept, n, cudaMemcpyHostToDevice, stream));
     SB_CUDA_CHECK(cudaMemcpyAsync(d_fsm_final, job.fsm_final, n, cudaMemcpyHostToDevice, stream));
+    cudaFree(d_tail_off);
+    cudaFree(d_tail_tok);
+    d_tail_off = nullptr, d_tail_tok = nullptr;
+    if (job.fsm_tail_off != nullptr) {
+      const size_t nt = job.fsm_tail_off[n];
+      if (dmalloc(&d_tail_off, n + 1) || dmalloc(&d_tail_tok, nt > 0 ? nt : 1)) return -1;
+      SB_CUDA_CHECK(cudaMemcpyAsync(d_tail_off, job.fsm_tail_off, (n + 1) * 4, cudaMemcpyHostToDevice,
+                                    stream));
+      if (nt)
+        SB_CUDA_CHECK(cudaMemcpyAsync(d_tail_tok, job.fsm_tail_tok, nt * 4, cudaMemcpyHostToDevice,
+                                      stream));
+    }
     return fsm_build_mask(d_fsm_trans, d_fsm_accept, static_cast<int>(n), d_tok_bytes, d_tok_off,
                           cfg.vocab, cfg.eos_id, d_mask_bits, mask_words, stream);
   }
@@ -417,6 +440,12 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
     return -1;
   }
   const int n_prefix = job.n_prefix, n_suffix = job.n_suffix;
+  const int n_forced = (has_fsm && job.n_forced_prefix > 0) ? job.n_forced_prefix : 0;
+  if (n_forced > n_suffix || (n_forced > 0 && n_forced >= max_new)) {
+    set_last_error("engine: forced output prefix (%d tokens) does not fit suffix/max_new_tokens",
+                   n_forced);
+    return -1;
+  }
   const int ctx_budget = c.max_position - max_new;  // prompt tokens that fit
   if (n_prefix + n_suffix + 1 > ctx_budget) {
     set_last_error("engine: system prompt + template (%d tokens) leave no room in the %d-token "
@@ -513,7 +542,10 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
     prof.launches[SB200_KC_OTHER] += 2;
     init_slots_kernel<<<n, 128, 0, stream>>>(d_seqs, d_pt, max_pages, page_table, slot_state,
                                              slot_ngen, slot_pos, slot_done, slot_row, slot_maxnew,
-                                             slot_next_tok);
+                                             slot_next_tok, d_suffix + (n_suffix - n_forced),
+                                             n_forced, embed_mode ? nullptr : job.out_tokens_dev,
+                                             embed_mode ? nullptr : job.out_len_dev,
+                                             job.max_new_tokens);
     prefill_prepare_kernel<<<n, 128, 0, stream>>>(d_seqs, d_prefix, n_prefix, d_suffix, n_suffix,
                                                   job.row_tokens_dev, job.row_tok_off_dev, tok_ids,
                                                   tok_pos, tok_slot, last_idx);

@@ -110,6 +110,8 @@ struct SampleArgs {
   const int32_t* fsm_trans;    // [n_states, 256] byte transitions, -1 = dead
   const uint8_t* fsm_accept;   // [n_states]
   const uint8_t* fsm_final;    // [n_states] accepting with no outgoing edge
+  const int32_t* fsm_tail_off; // [n_states+1] or null: forced terminal continuation per state
+  const int32_t* fsm_tail_tok;
   const uint8_t* tok_bytes;    // vocab byte blob
   const int32_t* tok_off;      // [vocab+1]
   int eos_id;

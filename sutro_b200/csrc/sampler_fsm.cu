@@ -98,7 +98,18 @@ __global__ void __launch_bounds__(kSampleThreads) sample_greedy_kernel(SampleArg
       const int b0 = a.tok_off[tok], b1 = a.tok_off[tok + 1];
       for (int i = b0; i < b1 && s >= 0; ++i) s = a.fsm_trans[s * 256 + a.tok_bytes[i]];
       a.slot_state[slot] = s;
-      if (s < 0 || a.fsm_final[s]) done = true;
+      if (s < 0 || a.fsm_final[s]) {
+        done = true;
+      } else if (a.fsm_tail_off != nullptr) {
+        // jump-forward: everything from here to a final state is forced -> emit it now
+        const int t0 = a.fsm_tail_off[s], t1 = a.fsm_tail_off[s + 1];
+        if (t1 > t0) {
+          const int maxnew = a.slot_maxnew[slot];
+          for (int i = t0; i < t1 && ngen < maxnew; ++i)
+            a.out_tokens[static_cast<size_t>(row) * a.out_stride + ngen++] = a.fsm_tail_tok[i];
+          done = true;
+        }
+      }
     }
   }
   if (ngen >= a.slot_maxnew[slot]) done = true;

@@ -55,6 +55,7 @@ class JobC(C.Structure):
                 ("truncate_rows", C.c_int),
                 ("fsm_trans", c_i32p), ("fsm_accept", c_u8p), ("fsm_final", c_u8p),
                 ("fsm_states", C.c_int), ("fsm_start", C.c_int),
+                ("n_forced_prefix", C.c_int), ("fsm_tail_off", c_i32p), ("fsm_tail_tok", c_i32p),
                 ("out_tokens_dev", C.c_void_p), ("out_len_dev", C.c_void_p),
                 ("out_embed_dev", C.c_void_p),
                 ("progress", PROGRESS_FN), ("progress_user", C.c_void_p), ("profile", C.c_int),
@@ -271,6 +272,7 @@ class LocalEngine:
             L.check(L.lib().sb200_engine_set_vocab(self._h, self.tokenizer._blob.ctypes.data,
                                                    self.tokenizer._off.ctypes.data))
         self._fsm_cache: Dict[str, ByteDFA] = {}
+        self._jump_cache: Dict[Any, Any] = {}
         self._tpl_cache: Dict[Any, Tuple[np.ndarray, np.ndarray]] = {}
 
     # ---- construction helpers -------------------------------------------
@@ -309,6 +311,31 @@ class LocalEngine:
             self._tpl_cache[key] = (pre, suf)
         return self._tpl_cache[key]
 
+    def _jump_plan(self, dfa: ByteDFA, key) -> Optional[Dict[str, Any]]:
+        """Jump-forward plan for a compiled schema (cached): canonical tokenisation of the
+        forced output prefix and of every forced terminal tail (GPU tokenizer)."""
+        if key in self._jump_cache:
+            return self._jump_cache[key]
+        plan = None
+        prefix, start_after, tails = dfa.forced_plan()
+        fully_forced = bool(dfa.final[start_after]) or start_after in tails
+        try:
+            texts = [prefix.decode("utf-8")] + [t.decode("utf-8") for t in tails.values()]
+        except UnicodeDecodeError:
+            texts = None
+        if texts is not None and not fully_forced and (prefix or tails):
+            enc = self.tokenizer.encode(texts)
+            off = np.zeros(dfa.n_states + 1, dtype=np.int32)
+            toks: List[int] = []
+            by_state = dict(zip(tails.keys(), enc[1:]))
+            for st in range(dfa.n_states):
+                toks += by_state.get(st, [])
+                off[st + 1] = len(toks)
+            plan = {"prefix_tokens": np.asarray(enc[0], dtype=np.int32), "start": int(start_after),
+                    "tail_off": off, "tail_tok": np.asarray(toks or [0], dtype=np.int32)}
+        self._jump_cache[key] = plan
+        return plan
+
     def compile_schema(self, schema: Dict[str, Any], limits: Optional[FsmLimits] = None) -> ByteDFA:
         import json
         key = json.dumps(schema, sort_keys=True) + repr(limits)
@@ -322,7 +349,8 @@ class LocalEngine:
                  fsm_limits: Optional[FsmLimits] = None,
                  progress: Optional[Callable[[int, int, int], None]] = None,
                  return_tokens: bool = False, return_text: bool = True,
-                 profile: bool = False, return_first_logits: bool = False) -> GenerationResult:
+                 profile: bool = False, return_first_logits: bool = False,
+                 jump_forward: bool = True) -> GenerationResult:
         """The whole hot path for one frame column.  Three phases, timed separately:
           A  host -> HBM   : rows -> Arrow blob, template/schema compile (cached), H2D copy
           B  device        : tokenize, prefill/decode (+mask), detokenize — HBM to HBM
@@ -342,6 +370,16 @@ class LocalEngine:
                                                 "output_tokens": 0, "rows_done": 0})
         pre, suf = self._template_tokens(system_prompt)
         dfa = self.compile_schema(json_schema, fsm_limits) if json_schema is not None else None
+        plan = None
+        if dfa is not None and jump_forward and not emb_mode:
+            # jump-forward decoding: bytes the automaton forces are not the model's choice —
+            # the forced output prefix rides with the prompt, forced terminal tails are
+            # appended by the sampler without another forward pass
+            plan = self._jump_plan(dfa, (id(dfa),))
+            if plan is not None and len(plan["prefix_tokens"]) >= max_new_tokens:
+                plan = None
+        if plan is not None:
+            suf = np.concatenate([suf, plan["prefix_tokens"]]).astype(np.int32)
         with torch.cuda.device(dev):
             d_text = (torch.from_numpy(np.ascontiguousarray(data)).to(dev) if n_bytes
                       else torch.zeros(1, dtype=torch.uint8, device=dev))
@@ -375,6 +413,11 @@ class LocalEngine:
                 job.fsm_accept = _np_ptr(dfa.accept, c_u8p)
                 job.fsm_final = _np_ptr(dfa.final, c_u8p)
                 job.fsm_states, job.fsm_start = dfa.n_states, dfa.start
+                if plan is not None:
+                    job.fsm_start = plan["start"]
+                    job.n_forced_prefix = len(plan["prefix_tokens"])
+                    job.fsm_tail_off = _np_ptr(plan["tail_off"], c_i32p)
+                    job.fsm_tail_tok = _np_ptr(plan["tail_tok"], c_i32p)
             job.out_tokens_dev = L.ptr(d_out)
             job.out_len_dev = L.ptr(d_len)
             job.out_embed_dev = L.ptr(d_emb)
@@ -437,6 +480,8 @@ class LocalEngine:
                      h2d_bytes=int(data.nbytes + off.nbytes), d2h_bytes=int(d2h),
                      t_h2d_s=t_a - t0, t_tokenize_s=t_tok - t_a, t_engine_s=t_run - t_tok,
                      t_detok_s=t_b - t_run, t_device_s=t_b - t_a, t_d2h_s=t_end - t_b,
-                     t_total_s=t_end - t0, fsm_states=0 if dfa is None else dfa.n_states)
+                     t_total_s=t_end - t0, fsm_states=0 if dfa is None else dfa.n_states,
+                     jump_forward=plan is not None,
+                     forced_prefix_tokens=0 if plan is None else int(len(plan["prefix_tokens"])))
         return GenerationResult(outputs, out_tokens, emb, stats,
                                 None if d_first is None else d_first.cpu())

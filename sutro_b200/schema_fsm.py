@@ -54,6 +54,36 @@ class ByteDFA:
         return bool(self.accept[s])
 
 
+    # ---- forced runs (jump-forward decoding) --------------------------------------
+    def forced_run(self, state: int):
+        """Follow `state` while exactly one byte keeps the automaton alive and the state is
+        not accepting (an accepting state is a decision: stop or continue).  Returns
+        (bytes, end_state)."""
+        out = bytearray()
+        s = state
+        while not self.accept[s]:
+            nxt = np.nonzero(self.trans[s] >= 0)[0]
+            if len(nxt) != 1:
+                break
+            out.append(int(nxt[0]))
+            s = int(self.trans[s, nxt[0]])
+        return bytes(out), s
+
+    def forced_plan(self):
+        """Jump-forward plan: the byte string every output must start with (+ the state
+        after it), and for every state whose continuation is forced all the way to a final
+        state, that terminal tail.  With constrained decoding the model has no say over
+        these bytes, so the engine feeds the prefix as part of the prompt and appends tails
+        without running the model (same strings, fewer decode steps)."""
+        prefix, start_after = self.forced_run(self.start)
+        tails = {}
+        for s in range(self.n_states):
+            run, end = self.forced_run(s)
+            if run and self.final[end]:
+                tails[s] = run
+        return prefix, start_after, tails
+
+
 # --------------------------------------------------------------------------- NFA
 class _NFA:
     def __init__(self):
