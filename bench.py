@@ -14,6 +14,11 @@ One "step" = one pass of the hot path over that frame on every rank (weak scalin
 each rank owns a 20k-row shard; rows are independent, there is no data-path
 collective — NCCL is used once, to broadcast the weights from rank 0).
 
+Decoding is greedy under the schema mask with jump-forward: bytes the automaton forces
+(`{"sentiment":"`, and e.g. `ositive"}` after a `p`) are fed with the prompt / appended
+instead of being decoded one token per forward pass; `output_tokens_per_sec` counts every
+emitted token, `model_decided_tokens_per_sec` only those that cost a forward pass.
+
 `value`  = rows/s with the frame's bytes already in HBM (tokenise -> prefill/decode ->
            detokenise, device to device), timed between device synchronisations.
 `e2e`    = rows/s through the public call with host buffers: Arrow bytes H2D, the same
@@ -316,6 +321,8 @@ def main():
     clk = clocks.stop()
     t_dev = sum(r.stats["t_device_s"] for r in results)
     n_out = sum(r.stats["output_tokens"] for r in results)
+    # tokens that cost a forward pass: one per row from the prefill logits + the decode steps
+    n_dec = sum(r.stats["decode_tokens"] + r.stats["n_rows"] for r in results)
     n_in = sum(r.stats["input_tokens"] for r in results)
     launches = sum(sum(r.stats["kernel_launches"].values()) + r.stats["tokenizer_launches"]
                    for r in results)
@@ -325,12 +332,13 @@ def main():
 
     # ---- max over ranks ----
     tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([float(n_out), float(n_in), float(launches)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([float(n_out), float(n_in), float(launches), float(n_dec)],
+                       dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     t_dev_max, t_e2e_max = tt.tolist()
-    n_out_all, n_in_all, launches_all = cnt.tolist()
+    n_out_all, n_in_all, launches_all, n_dec_all = cnt.tolist()
     total_rows = args.rows * args.steps * world
 
     # ---- one extra profiled step: per-kernel-class device time (CUDA events on the
@@ -379,6 +387,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, args.rows),
             "output_tokens_per_sec": n_out_all / t_dev_max,
+            "model_decided_tokens_per_sec": n_dec_all / t_dev_max,
             "input_tokens_per_sec": n_in_all / t_dev_max,
             "e2e": {"value": total_rows / t_e2e_max, "unit": "rows/s",
                     "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"],
