@@ -86,6 +86,20 @@ init_slots_kernel(const SeqInit* __restrict__ seqs, const int32_t* __restrict__ 
   }
 }
 
+// Seed the first own page of newly admitted rows with the partially filled last page of the
+// shared prefix (all layers, all kv heads): sharing is page-granular, but the tail of the
+// prefix need not be recomputed per row — a 2.3 MB copy replaces up to 15 tokens of prefill.
+__global__ void __launch_bounds__(256)
+copy_prefix_page_kernel(__nv_bfloat16* __restrict__ kv_pool, size_t layer_stride,
+                        size_t page_elems, int src_page, const int32_t* __restrict__ dst_pages) {
+  const int dst = dst_pages[blockIdx.x];
+  if (dst < 0) return;
+  __nv_bfloat16* base = kv_pool + static_cast<size_t>(blockIdx.y) * layer_stride;
+  const uint4* s = reinterpret_cast<const uint4*>(base + static_cast<size_t>(src_page) * page_elems);
+  uint4* d = reinterpret_cast<uint4*>(base + static_cast<size_t>(dst) * page_elems);
+  for (size_t i = threadIdx.x; i < page_elems / 8; i += blockDim.x) d[i] = s[i];
+}
+
 __global__ void scatter_embed_kernel(const float* __restrict__ src, const SeqInit* __restrict__ seqs,
                                      float* __restrict__ dst, int d) {
   const int row = seqs[blockIdx.x].row;
@@ -257,7 +271,7 @@ struct Engine {
     SB_CUDA_CHECK(cudaMemsetAsync(page_table, 0, S * max_pages * sizeof(int32_t), stream));
     SB_CUDA_CHECK(cudaMemsetAsync(slot_done, 0, S * sizeof(int32_t), stream));
     stage_cap = (sizeof(SeqInit) / 4) * S + static_cast<size_t>(S) * max_pages + 2 * (T / 16 + S) +
-                4 * S + 64;
+                5 * S + 64;
     SB_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_stage), stage_cap * 4));
     if (dmalloc(&d_stage, stage_cap)) return -1;
     SB_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&h_done), S * 4));
@@ -502,10 +516,13 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
   int32_t* h_pt = h_stage + seq_words;
   int32_t* h_work = h_pt + static_cast<size_t>(S + 2) * max_pages;
   int32_t* h_misc = h_work + 2 * (t_max / 16 + S + 2);  // seq_slot|q_start|q_len|past : 4*(S+2)
+  int32_t* h_copy = h_misc + 4 * (S + 2);               // first own page to seed, or -1
   const SeqInit* d_seqs = reinterpret_cast<const SeqInit*>(d_stage);
   const int32_t* d_pt = d_stage + seq_words;
   const int32_t* d_work = d_pt + static_cast<size_t>(S + 2) * max_pages;
   const int32_t* d_misc = d_work + 2 * (t_max / 16 + S + 2);
+  const int32_t* d_copy = d_misc + 4 * (S + 2);
+  int prefix_tail_page = -1;  // physical page holding the partial tail of the shared prefix
 
   std::vector<int32_t> prefix_pages;
   std::vector<std::vector<int32_t>> slot_pages(S);
@@ -549,6 +566,12 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
     prefill_prepare_kernel<<<n, 128, 0, stream>>>(d_seqs, d_prefix, n_prefix, d_suffix, n_suffix,
                                                   job.row_tokens_dev, job.row_tok_off_dev, tok_ids,
                                                   tok_pos, tok_slot, last_idx);
+    if (prefix_tail_page >= 0 && sample) {
+      ++prof.launches[SB200_KC_OTHER];
+      copy_prefix_page_kernel<<<dim3(n, c.n_layers), 256, 0, stream>>>(
+          kv_pool, layer_stride, static_cast<size_t>(c.n_kv_heads) * 2 * kTileElems,
+          prefix_tail_page, d_copy);
+    }
     SB_CUDA_CHECK(cudaGetLastError());
     if (forward(T, true, n, d_work, n_work, d_misc, d_misc + (S + 2), d_misc + 2 * (S + 2),
                 d_misc + 3 * (S + 2)))
@@ -566,15 +589,15 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
   };
 
   // ---- shared prefix: compute its KV once, every row's page table points at it ----
-  const int prefix_cached = (job.share_prefix && n_prefix >= kPageTokens)
-                                ? (n_prefix / kPageTokens) * kPageTokens
-                                : 0;
+  // The whole prefix is computed once; full pages are shared through the page tables and
+  // the partially filled last page is copied into each row's first own page.
+  const int prefix_cached = (job.share_prefix && n_prefix >= kPageTokens) ? n_prefix : 0;
   if (prefix_cached > 0) {
     if (prefix_cached > c.max_prefill_tokens) {
       set_last_error("engine: shared prefix (%d tokens) exceeds max_prefill_tokens", prefix_cached);
       return -1;
     }
-    const int np = prefix_cached / kPageTokens;
+    const int np = (prefix_cached + kPageTokens - 1) / kPageTokens;
     if (static_cast<int64_t>(free_pages.size()) < np) {
       set_last_error("engine: KV pool too small for the shared prefix");
       return -1;
@@ -590,6 +613,7 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
       release_all();
       return -1;
     }
+    if (prefix_cached % kPageTokens != 0) prefix_tail_page = prefix_pages.back();
     SB_CUDA_CHECK(cudaStreamSynchronize(stream));
   }
 
@@ -607,7 +631,8 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
         set_last_error("engine: row %lld renders to an empty prompt", (long long)r);
         return -1;
       }
-      const int past = std::min(prefix_cached, ((P - 1) / kPageTokens) * kPageTokens);
+      int past = std::min(prefix_cached, P - 1);
+      if (past < prefix_cached) past = (past / kPageTokens) * kPageTokens;  // prompt ends inside the prefix
       const int q_len = P - past;
       if (T + q_len > c.max_prefill_tokens) {
         if (n == 0) {
@@ -633,11 +658,14 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
       std::fill(pt, pt + max_pages, 0);
       for (int i = 0; i < past / kPageTokens; ++i) pt[i] = prefix_pages[i];
       auto& mine = slot_pages[slot];
+      h_copy[n] = -1;
       for (int i = 0; i < own; ++i) {
         mine.push_back(free_pages.back());
         pt[past / kPageTokens + i] = free_pages.back();
         free_pages.pop_back();
       }
+      // positions [16*(past/16), past) of the first own page hold prefix tokens: seed them
+      if (past % kPageTokens != 0) h_copy[n] = pt[past / kPageTokens];
       h_seqs[n] = SeqInit{slot, static_cast<int32_t>(r), T, q_len, past, n_row_tok[r], max_new,
                           has_fsm ? job.fsm_start : -1};
       slot_live[slot] = 1;
