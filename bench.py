@@ -105,6 +105,16 @@ def log(msg: str):
         print(f"[bench +{time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
+# stdout must carry exactly one JSON line: libraries that print there (NCCL's version
+# banner) are diverted to stderr for the life of the process; emit() writes to the real fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def make_rows(n: int, seed: int):
     from sutro_b200 import synth
     return synth.product_reviews(n, seed=seed)
@@ -212,7 +222,7 @@ def run_reference_arm(args):
             "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "setup_s": setup}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, rows_per_gpu):
@@ -406,7 +416,7 @@ def main():
             "setup_s": setup_s, "weight_broadcast_ms": bcast_ms,
             "kv_pages": eng.kv_pages,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
