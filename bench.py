@@ -107,12 +107,24 @@ def log(msg: str):
 
 # stdout must carry exactly one JSON line: libraries that print there (NCCL's version
 # banner) are diverted to stderr for the life of the process; emit() writes to the real fd.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def divert_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line: dict):
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def make_rows(n: int, seed: int):
@@ -258,6 +270,7 @@ def main():
                     help="KV pool size in pages (default: 80%% of free memory); small pools keep "
                          "ncu's save/restore cheap")
     args = ap.parse_args()
+    divert_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
