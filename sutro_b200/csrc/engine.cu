@@ -284,7 +284,7 @@ struct Engine {
   // ---- one pass of the transformer stack over T flattened tokens -----------
   // prefill: attention over (cached prefix | new tokens) per sequence;
   // decode : one token per sequence against its paged history.
-  int forward(int T, bool prefill, int n_seq, const int32_t* d_work, int n_work,
+  int forward(int T, bool prefill, const int32_t* d_work, int n_work,
               const int32_t* d_seq_slot, const int32_t* d_seq_q_start, const int32_t* d_seq_q_len,
               const int32_t* d_seq_past) {
     const auto& c = cfg;
@@ -329,7 +329,6 @@ struct Engine {
       SB_K(SB200_KC_GEMM, gemm(act, wd[l], x, x, T, c.d_model, c.d_ff, c.d_model,
                                EPI_RESIDUAL_BF16));
     }
-    (void)n_seq;
     return 0;
   }
 
@@ -510,7 +509,7 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
 
   // staging layout (int32 units)
   const int S = c.max_slots;
-  const int prefix_slot = S, dummy_slot = S + 1;
+  const int prefix_slot = S;  // page-table row S holds the shared prefix
   SeqInit* h_seqs = reinterpret_cast<SeqInit*>(h_stage);
   const size_t seq_words = (sizeof(SeqInit) / 4) * (S + 2);
   int32_t* h_pt = h_stage + seq_words;
@@ -529,7 +528,6 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
   std::vector<int32_t> free_slots;
   for (int s = S - 1; s >= 0; --s) free_slots.push_back(s);
   std::vector<int32_t> active;  // slots in the decode batch
-  std::vector<uint8_t> slot_live(S, 0);
   std::vector<int32_t> slot_ctx(S, 0);  // host mirror: position of the next fed token
 
   auto release_all = [&]() {
@@ -573,7 +571,7 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
           prefix_tail_page, d_copy);
     }
     SB_CUDA_CHECK(cudaGetLastError());
-    if (forward(T, true, n, d_work, n_work, d_misc, d_misc + (S + 2), d_misc + 2 * (S + 2),
+    if (forward(T, true, d_work, n_work, d_misc, d_misc + (S + 2), d_misc + 2 * (S + 2),
                 d_misc + 3 * (S + 2)))
       return -1;
     if (!sample) return 0;
@@ -619,7 +617,6 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
 
   int64_t next_row = 0, rows_done = 0, in_tokens = 0, steps_prefill = 0, steps_decode = 0;
   int64_t decode_tokens = 0, prefill_tokens = prefix_cached;
-  const int pages_shared = prefix_cached / kPageTokens;
   int rc = 0;
 
   auto admit = [&]() -> int {  // returns number of rows admitted, <0 on error
@@ -668,7 +665,6 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
       if (past % kPageTokens != 0) h_copy[n] = pt[past / kPageTokens];
       h_seqs[n] = SeqInit{slot, static_cast<int32_t>(r), T, q_len, past, n_row_tok[r], max_new,
                           has_fsm ? job.fsm_start : -1};
-      slot_live[slot] = 1;
       slot_ctx[slot] = P;
       T += q_len;
       in_tokens += P;
@@ -692,7 +688,6 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
       if (h_done[s]) {
         for (int32_t p : slot_pages[s]) free_pages.push_back(p);
         slot_pages[s].clear();
-        slot_live[s] = 0;
         free_slots.push_back(s);
         ++rows_done;
       } else {
@@ -702,8 +697,6 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
     active.resize(k);
     return 0;
   };
-  (void)pages_shared;
-  (void)dummy_slot;
 
   const int min_admit = std::max(1, c.min_admit_rows);
   while (rows_done < N) {
@@ -752,7 +745,7 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
     const int prc = prepare_decode(row_slot, slot_next_tok, slot_pos, tok_ids, tok_pos, tok_slot,
                                    ctx_len, B, stream);
     prof.end();
-    if (prc || forward(B, false, B, nullptr, 0, nullptr, nullptr, nullptr, nullptr) ||
+    if (prc || forward(B, false, nullptr, 0, nullptr, nullptr, nullptr, nullptr) ||
         head_and_sample(B, nullptr, row_slot, job, has_fsm)) {
       rc = -1;
       break;
@@ -826,20 +819,19 @@ int sb200_engine_create(const sb200_engine_config* cfg, const sb200_engine_weigh
   e->cfg = *cfg;
   e->w = *w;
   const int L = cfg->n_layers;
-  auto cp = [&](std::vector<const void*>& v, const void* const* src, bool optional) {
+  auto cp = [&](std::vector<const void*>& v, const void* const* src) {
     v.assign(L, nullptr);
     if (src)
       for (int i = 0; i < L; ++i) v[i] = src[i];
-    (void)optional;
   };
-  cp(e->ln1, w->ln1, false);
-  cp(e->ln2, w->ln2, false);
-  cp(e->wqkv, w->wqkv, false);
-  cp(e->wo, w->wo, false);
-  cp(e->wgu, w->wgu, false);
-  cp(e->wd, w->wd, false);
-  cp(e->qn, cfg->qk_norm ? w->q_norm : nullptr, true);
-  cp(e->kn, cfg->qk_norm ? w->k_norm : nullptr, true);
+  cp(e->ln1, w->ln1);
+  cp(e->ln2, w->ln2);
+  cp(e->wqkv, w->wqkv);
+  cp(e->wo, w->wo);
+  cp(e->wgu, w->wgu);
+  cp(e->wd, w->wd);
+  cp(e->qn, cfg->qk_norm ? w->q_norm : nullptr);
+  cp(e->kn, cfg->qk_norm ? w->k_norm : nullptr);
   for (int i = 0; i < L; ++i) {
     if (!e->ln1[i] || !e->ln2[i] || !e->wqkv[i] || !e->wo[i] || !e->wgu[i] || !e->wd[i] ||
         (cfg->qk_norm && (!e->qn[i] || !e->kn[i]))) {
