@@ -187,6 +187,14 @@ typedef struct {
   int profile;                    /* 1: time every kernel launch with CUDA events        */
   float* out_first_logits_dev;    /* optional [n_rows, vocab]: fp32 logits of each row's first
                                      decision (teacher-forced parity checks); NULL = off   */
+  /* payload["sampling_params"] / payload["random_seed_per_input"] (sutro/sdk.py:203-204)  */
+  float temperature;              /* 0 = greedy                                          */
+  int top_k;                      /* <= 0 = off                                          */
+  float top_p;                    /* >= 1 = off (0 is treated as off too)                */
+  uint64_t seed;
+  int seed_per_row;               /* 1: every row draws from its own Philox stream       */
+  float* out_cum_logprob_dev;     /* optional [n_rows]: sum of log p(token) under the masked
+                                     softmax at the sampling temperature; NULL = off      */
 } sb200_job;
 
 /* kernel classes for the per-class launch counts / device times in sb200_job_stats */

@@ -65,7 +65,7 @@ init_slots_kernel(const SeqInit* __restrict__ seqs, const int32_t* __restrict__ 
                   int32_t* slot_ngen, int32_t* slot_pos, int32_t* slot_done, int32_t* slot_row,
                   int32_t* slot_maxnew, int32_t* slot_next_tok, const int32_t* __restrict__ forced,
                   int n_forced, int32_t* __restrict__ out_tokens, int32_t* __restrict__ out_len,
-                  int out_stride) {
+                  int out_stride, float* __restrict__ slot_cum_logprob) {
   const SeqInit s = seqs[blockIdx.x];
   for (int i = threadIdx.x; i < max_pages; i += blockDim.x)
     page_table[static_cast<size_t>(s.slot) * max_pages + i] =
@@ -83,6 +83,7 @@ init_slots_kernel(const SeqInit* __restrict__ seqs, const int32_t* __restrict__ 
     slot_row[s.slot] = s.row;
     slot_maxnew[s.slot] = s.max_new;
     slot_next_tok[s.slot] = 0;
+    slot_cum_logprob[s.slot] = 0.f;
   }
 }
 
@@ -195,6 +196,7 @@ struct Engine {
           *row_slot = nullptr, *last_idx = nullptr, *page_table = nullptr;
   int32_t *slot_state = nullptr, *slot_ngen = nullptr, *slot_next_tok = nullptr,
           *slot_pos = nullptr, *slot_done = nullptr, *slot_row = nullptr, *slot_maxnew = nullptr;
+  float* slot_cum_logprob = nullptr;
   // staging
   int32_t *h_stage = nullptr, *d_stage = nullptr;
   size_t stage_cap = 0;  // int32 elements
@@ -224,7 +226,7 @@ struct Engine {
                     (void*)tok_pos, (void*)tok_slot, (void*)ctx_len, (void*)row_slot,
                     (void*)last_idx, (void*)page_table, (void*)slot_state, (void*)slot_ngen,
                     (void*)slot_next_tok, (void*)slot_pos, (void*)slot_done, (void*)slot_row,
-                    (void*)slot_maxnew, (void*)d_stage, (void*)d_tok_bytes, (void*)d_tok_off,
+                    (void*)slot_maxnew, (void*)slot_cum_logprob, (void*)d_stage, (void*)d_tok_bytes, (void*)d_tok_off,
                     (void*)d_fsm_trans, (void*)d_fsm_accept, (void*)d_fsm_final,
                     (void*)d_mask_bits, (void*)d_prefix, (void*)d_suffix, (void*)d_tail_off,
                     (void*)d_tail_tok})
@@ -259,7 +261,7 @@ struct Engine {
         dmalloc(&ctx_len, S) || dmalloc(&row_slot, S) || dmalloc(&last_idx, S) ||
         dmalloc(&page_table, S * max_pages) || dmalloc(&slot_state, S) || dmalloc(&slot_ngen, S) ||
         dmalloc(&slot_next_tok, S) || dmalloc(&slot_pos, S) || dmalloc(&slot_done, S) ||
-        dmalloc(&slot_row, S) || dmalloc(&slot_maxnew, S))
+        dmalloc(&slot_row, S) || dmalloc(&slot_maxnew, S) || dmalloc(&slot_cum_logprob, S))
       return -1;
     if (c.embedding_model) {
       if (dmalloc(&embed_tmp, static_cast<size_t>(c.max_slots) * c.d_model)) return -1;
@@ -382,6 +384,13 @@ struct Engine {
       a.tok_off = d_tok_off;
       a.eos_id = c.eos_id;
       a.ignore_eos = job.ignore_eos;
+      a.temperature = job.temperature > 0.f ? job.temperature : 0.f;
+      a.top_k = job.top_k;
+      a.top_p = (job.top_p > 0.f && job.top_p < 1.f) ? job.top_p : 1.f;
+      a.seed = job.seed;
+      a.seed_per_row = job.seed_per_row;
+      a.slot_cum_logprob = job.out_cum_logprob_dev ? slot_cum_logprob : nullptr;
+      a.out_cum_logprob = job.out_cum_logprob_dev;
       SB_K(SB200_KC_SAMPLE, sample_greedy(a, stream));
     }
     return 0;
@@ -560,7 +569,7 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
                                              slot_next_tok, d_suffix + (n_suffix - n_forced),
                                              n_forced, embed_mode ? nullptr : job.out_tokens_dev,
                                              embed_mode ? nullptr : job.out_len_dev,
-                                             job.max_new_tokens);
+                                             job.max_new_tokens, slot_cum_logprob);
     prefill_prepare_kernel<<<n, 128, 0, stream>>>(d_seqs, d_prefix, n_prefix, d_suffix, n_suffix,
                                                   job.row_tokens_dev, job.row_tok_off_dev, tok_ids,
                                                   tok_pos, tok_slot, last_idx);

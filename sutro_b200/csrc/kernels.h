@@ -116,8 +116,16 @@ struct SampleArgs {
   const int32_t* tok_off;      // [vocab+1]
   int eos_id;
   int ignore_eos;
+  // sampling_params (reference: opaque dict forwarded to the service, sutro/sdk.py:203)
+  float temperature;       // 0 = greedy (arg-max, lowest index wins ties)
+  int top_k;               // <= 0: off
+  float top_p;             // >= 1: off
+  uint64_t seed;
+  int seed_per_row;        // random_seed_per_input (sutro/sdk.py:204): 1 = own stream per row
+  float* slot_cum_logprob; // nullable: running sum of log p(token) under the masked softmax
+  float* out_cum_logprob;  // [n_rows], written together with out_len
 };
-int sample_greedy(const SampleArgs& a, cudaStream_t stream);
+int sample_greedy(const SampleArgs& a, cudaStream_t stream);  // dispatches on a.temperature
 int prepare_decode(const int32_t* row_slot, const int32_t* slot_next_tok, const int32_t* slot_pos,
                    int32_t* tok_ids, int32_t* tok_pos, int32_t* tok_slot, int32_t* ctx_len, int B,
                    cudaStream_t stream);

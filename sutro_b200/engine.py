@@ -59,7 +59,10 @@ class JobC(C.Structure):
                 ("out_tokens_dev", C.c_void_p), ("out_len_dev", C.c_void_p),
                 ("out_embed_dev", C.c_void_p),
                 ("progress", PROGRESS_FN), ("progress_user", C.c_void_p), ("profile", C.c_int),
-                ("out_first_logits_dev", C.c_void_p)]
+                ("out_first_logits_dev", C.c_void_p),
+                ("temperature", C.c_float), ("top_k", C.c_int), ("top_p", C.c_float),
+                ("seed", C.c_uint64), ("seed_per_row", C.c_int),
+                ("out_cum_logprob_dev", C.c_void_p)]
 
 
 KERNEL_CLASSES = ["gemm", "attn_decode", "attn_prefill", "norm", "rope", "sample", "embed",
@@ -216,6 +219,7 @@ class GenerationResult:
     embeddings: Optional[np.ndarray]
     stats: Dict[str, Any] = field(default_factory=dict)
     first_logits: Optional[Any] = None   # torch fp32 [n_rows, vocab] (debug/parity only)
+    cum_logprobs: Optional[np.ndarray] = None  # fp32 [n_rows] when return_logprobs=True
 
 
 class LocalEngine:
@@ -350,7 +354,9 @@ class LocalEngine:
                  progress: Optional[Callable[[int, int, int], None]] = None,
                  return_tokens: bool = False, return_text: bool = True,
                  profile: bool = False, return_first_logits: bool = False,
-                 jump_forward: bool = True) -> GenerationResult:
+                 jump_forward: bool = True, temperature: float = 0.0, top_k: int = 0,
+                 top_p: float = 1.0, seed: int = 0, seed_per_row: bool = False,
+                 return_logprobs: bool = False) -> GenerationResult:
         """The whole hot path for one frame column.  Three phases, timed separately:
           A  host -> HBM   : rows -> Arrow blob, template/schema compile (cached), H2D copy
           B  device        : tokenize, prefill/decode (+mask), detokenize — HBM to HBM
@@ -427,6 +433,12 @@ class LocalEngine:
             if return_first_logits and not emb_mode:
                 d_first = torch.zeros(n_rows, self.spec.vocab_size, dtype=torch.float32, device=dev)
                 job.out_first_logits_dev = d_first.data_ptr()
+            job.temperature, job.top_k, job.top_p = float(temperature), int(top_k), float(top_p)
+            job.seed, job.seed_per_row = int(seed) & (2 ** 64 - 1), int(seed_per_row)
+            d_lp = None
+            if return_logprobs and not emb_mode:
+                d_lp = torch.zeros(n_rows, dtype=torch.float32, device=dev)
+                job.out_cum_logprob_dev = d_lp.data_ptr()
             st = JobStatsC()
             torch.cuda.synchronize(dev)
             t_tok = time.perf_counter()
@@ -484,4 +496,5 @@ class LocalEngine:
                      jump_forward=plan is not None,
                      forced_prefix_tokens=0 if plan is None else int(len(plan["prefix_tokens"])))
         return GenerationResult(outputs, out_tokens, emb, stats,
-                                None if d_first is None else d_first.cpu())
+                                None if d_first is None else d_first.cpu(),
+                                None if d_lp is None else d_lp.cpu().numpy())

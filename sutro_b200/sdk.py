@@ -47,6 +47,7 @@ class _Job:
         self.embeddings = None
         self.stats: Dict[str, Any] = {}
         self.failure_reason: Optional[str] = None
+        self.cum_logprobs = None
         self.created = time.time()
         self.cost_estimate: Optional[float] = None
 
@@ -93,14 +94,21 @@ class Sutro(BaseSutroClient):
             raise ValueError(
                 f"Job description cannot exceed {JOB_DESCRIPTION_CHAR_LIMIT} characters.")
         input_data = handle_data_helper(data, column)
+        # sampling_params is an opaque dict in the reference (forwarded as is, sdk.py:203);
+        # the local engine understands the usual keys and rejects the rest loudly.
         sp = dict(sampling_params or {})
-        temperature = sp.get("temperature", 0) or 0
-        if temperature != 0 or sp.get("top_p", 1) not in (1, 1.0, None) or \
-                sp.get("top_k", -1) not in (-1, 0, None):
-            raise ValueError("the local engine decodes greedily; sampling_params may only set "
-                             "max_tokens / max_new_tokens / ignore_eos (temperature 0)")
-        if random_seed_per_input:
-            self._say("random_seed_per_input has no effect under greedy decoding")
+        known = {"temperature", "top_p", "top_k", "seed", "random_seed", "max_tokens",
+                 "max_new_tokens", "ignore_eos"}
+        unknown = sorted(set(sp) - known)
+        if unknown:
+            raise ValueError(f"unsupported sampling_params for the local engine: {unknown} "
+                             f"(supported: {sorted(known)})")
+        temperature = float(sp.get("temperature") or 0.0)
+        top_p = float(sp.get("top_p") if sp.get("top_p") is not None else 1.0)
+        top_k = int(sp.get("top_k") if sp.get("top_k") not in (None, -1) else 0)
+        if temperature < 0 or not (0.0 < top_p <= 1.0) or top_k < 0:
+            raise ValueError("sampling_params: temperature >= 0, 0 < top_p <= 1, top_k >= 0")
+        seed = int(sp.get("seed", sp.get("random_seed", 0)) or 0)
         max_new = int(sp.get("max_tokens", sp.get("max_new_tokens", 64)))
 
         job = _Job("job-" + uuid.uuid4().hex[:24], model, len(input_data), name, description,
@@ -126,7 +134,9 @@ class Sutro(BaseSutroClient):
             t0 = time.perf_counter()
             res = eng.generate(input_data, system_prompt=system_prompt, json_schema=json_schema,
                                max_new_tokens=max_new, ignore_eos=bool(sp.get("ignore_eos", False)),
-                               truncate_rows=truncate_rows)
+                               truncate_rows=truncate_rows, temperature=temperature, top_k=top_k,
+                               top_p=top_p, seed=seed, seed_per_row=bool(random_seed_per_input),
+                               return_logprobs=True)
             dt = time.perf_counter() - t0
         except KeyboardInterrupt:
             job.status = JobStatus.CANCELLED
@@ -140,6 +150,7 @@ class Sutro(BaseSutroClient):
             return None
         job.inputs = input_data
         job.stats = res.stats
+        job.cum_logprobs = getattr(res, "cum_logprobs", None)
         if res.embeddings is not None:
             job.embeddings = res.embeddings
             job.outputs = [row.tolist() for row in res.embeddings]
@@ -273,13 +284,15 @@ class Sutro(BaseSutroClient):
         if j.status != JobStatus.SUCCEEDED or j.outputs is None:
             self._say(f"Job {job_id} has no results (status {j.status.value})", "fail")
             return None
-        if include_cumulative_logprobs:
-            raise ValueError("cumulative logprobs are not produced by the local greedy engine")
+        if include_cumulative_logprobs and j.cum_logprobs is None:
+            raise ValueError("this job recorded no cumulative logprobs (embedding job?)")
         path = os.path.join(self.cache_dir, f"{job_id}.snappy.parquet")
         cols: Dict[str, Any] = {}
         if include_inputs:
             cols["inputs"] = j.inputs
         cols[output_column] = j.outputs
+        if include_cumulative_logprobs:
+            cols["cumulative_logprobs"] = [float(x) for x in j.cum_logprobs]
         df = pd.DataFrame(cols)
         if not disable_cache:
             try:

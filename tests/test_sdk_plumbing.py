@@ -131,9 +131,33 @@ def test_engine_failure_prints_and_returns_none():        # non-200 convention, 
     assert c.list_jobs()[0]["status"] == "FAILED"
 
 
-def test_non_greedy_sampling_is_rejected():
-    with pytest.raises(ValueError, match="greedily"):
-        client().infer(["x"], model="qwen-3-4b", sampling_params={"temperature": 0.7})
+def test_sampling_params_are_mapped_and_unknown_keys_rejected():
+    c = client()
+    c.infer(["x"], model="qwen-3-4b", sampling_params={"temperature": 0.7, "top_p": 0.9,
+                                                        "top_k": 40, "seed": 5, "max_tokens": 12},
+            random_seed_per_input=True)
+    kw = c._engines["qwen-3-4b"].calls[0][1]
+    assert (kw["temperature"], kw["top_p"], kw["top_k"], kw["seed"], kw["max_new_tokens"]) == \
+        (0.7, 0.9, 40, 5, 12)
+    assert kw["seed_per_row"] is True
+    with pytest.raises(ValueError, match="unsupported sampling_params"):
+        client().infer(["x"], model="qwen-3-4b", sampling_params={"beam_width": 4})
+    with pytest.raises(ValueError, match="top_p"):
+        client().infer(["x"], model="qwen-3-4b", sampling_params={"top_p": 0})
+
+
+def test_cumulative_logprobs_column():
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+
+    class E:
+        def generate(self, rows, **kw):
+            return GenerationResult([f"o{i}" for i in range(len(rows))], None, None, {},
+                                    None, np.array([-1.5, -0.25], dtype=np.float32))
+    c.register_engine("qwen-3-4b", E())
+    jid = c.infer(["a", "b"], model="qwen-3-4b", stay_attached=False)
+    df = c.get_job_results(jid, include_cumulative_logprobs=True, include_inputs=True)
+    assert list(df.columns) == ["inputs", "inference_result", "cumulative_logprobs"]
+    assert list(df["cumulative_logprobs"]) == [-1.5, -0.25]
 
 
 def test_infer_per_model_returns_list_of_ids():           # sutro/sdk.py:750-757
