@@ -279,7 +279,7 @@ def main():
                          "decode-attention-heavy secondary measurement")
     ap.add_argument("--max-slots", type=int, default=3584,
                     help="decode slots; 3584 = 14 x 256 rows quantises the CTA-pair GEMM tiles well")
-    ap.add_argument("--max-prefill-tokens", type=int, default=16384)
+    ap.add_argument("--max-prefill-tokens", type=int, default=32768)
     ap.add_argument("--cpu-rows", type=int, default=8, help="max rows in the CPU-baseline sample")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0,
                     help="stop the CPU-baseline sample after this many seconds of CPU work")
