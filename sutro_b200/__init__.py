@@ -19,7 +19,7 @@ from .sdk import Sutro  # noqa: F401
 _instance = None
 _PUBLIC = ["infer", "infer_per_model", "await_job_completion", "get_job_results",
            "get_job_status", "fetch_job", "list_jobs", "cancel_job", "get_job_embeddings",
-           "register_engine"]
+           "register_engine", "classify", "embed", "score"]
 
 
 def _client() -> Sutro:

@@ -32,6 +32,7 @@ import pandas as pd
 from .common import (ModelOptions, handle_data_helper, is_frame, normalize_output_schema, pl,
                      to_colored_text)
 from .interfaces import BaseSutroClient, JobStatus
+from .templates import Templates
 
 JOB_NAME_CHAR_LIMIT = 45          # sutro/sdk.py:39-40
 JOB_DESCRIPTION_CHAR_LIMIT = 512
@@ -52,7 +53,7 @@ class _Job:
         self.cost_estimate: Optional[float] = None
 
 
-class Sutro(BaseSutroClient):
+class Sutro(Templates, BaseSutroClient):
     def __init__(self, devices: Optional[List[int]] = None, weights_seed: int = 0,
                  engine_options: Optional[Dict[str, Any]] = None, cache_dir: Optional[str] = None,
                  verbose: bool = True):

@@ -175,3 +175,81 @@ def test_rows_to_blob_roundtrip_arrow_style():
     import pyarrow as pa
     d2, o2 = rows_to_blob(pa.array(["a", "bc"]).slice(1))
     assert blob_to_rows(d2, o2) == ["bc"]
+
+
+# --------------------------------------------------------------------------- templates
+class SchemaEcho:
+    """Stub engine that answers according to the schema it was given."""
+    def __init__(self):
+        self.calls = []
+
+    def generate(self, rows, **kw):
+        self.calls.append((list(rows), kw))
+        props = (kw.get("json_schema") or {}).get("properties", {})
+        outs = []
+        for i, _ in enumerate(rows):
+            obj = {}
+            for k, sch in props.items():
+                if "enum" in sch:
+                    obj[k] = sch["enum"][i % len(sch["enum"])]
+                elif sch.get("type") == "integer":
+                    obj[k] = sch["minimum"] + i % (sch["maximum"] - sch["minimum"] + 1)
+                else:
+                    obj[k] = f"t{i}"
+            outs.append(json.dumps(obj))
+        return GenerationResult(outs, None, None, {})
+
+
+def test_template_signatures_match_reference():
+    assert list(inspect.signature(Sutro.classify).parameters) == [
+        "self", "data", "classes", "model", "job_priority", "name", "description",
+        "output_column", "column", "truncate_rows", "include_scratchpad"]
+    assert list(inspect.signature(Sutro.embed).parameters) == [
+        "self", "data", "model", "job_priority", "name", "description", "output_column",
+        "column", "truncate_rows"]
+    assert list(inspect.signature(Sutro.score).parameters) == [
+        "self", "data", "model", "job_priority", "name", "description", "column", "criteria",
+        "score_column_name", "range"]
+    assert inspect.signature(Sutro.embed).parameters["model"].default == "qwen-3-embedding-0.6b"
+
+
+def test_classify_constrains_to_the_label_set():
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+    eng = SchemaEcho()
+    c.register_engine("m", eng)
+    df = pd.DataFrame({"t": ["a", "b", "c"]})
+    out = c.classify(df, {"pos": "happy", "neg": "unhappy"}, model="m", column="t")
+    assert list(out.columns) == ["inference_result"] and list(out["inference_result"]) == ["pos", "neg", "pos"]
+    kw = eng.calls[0][1]
+    assert kw["json_schema"]["properties"]["classification"]["enum"] == ["pos", "neg"]
+    assert "happy" in kw["system_prompt"]
+    full = c.classify(df, ["x", "y"], model="m", column="t", include_scratchpad=True)
+    assert list(full.columns) == ["scratchpad", "classification"]
+    with pytest.raises(ValueError):
+        c.classify(df, [], model="m", column="t")
+
+
+def test_score_appends_bounded_integer_column():
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+    eng = SchemaEcho()
+    c.register_engine("m", eng)
+    df = pd.DataFrame({"t": ["a", "b", "c"]})
+    out = c.score(df, model="m", column="t", criteria=["clarity", "tone"], range=(1, 5),
+                  score_column_name="s")
+    assert list(out.columns) == ["t", "s"] and list(out["s"]) == [1, 2, 3]
+    sch = eng.calls[0][1]["json_schema"]["properties"]["s"]
+    assert (sch["minimum"], sch["maximum"]) == (1, 5)
+    assert "t" in df.columns and "s" not in df.columns       # input frame is not mutated
+    with pytest.raises(ValueError):
+        c.score(df, model="m", column="t")
+
+
+def test_embed_returns_vector_column():
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+
+    class Emb:
+        def generate(self, rows, **kw):
+            return GenerationResult(None, None, np.eye(len(rows), 4, dtype=np.float32), {})
+    c.register_engine("qwen-3-embedding-0.6b", Emb())
+    out = c.embed(["a", "b"])
+    assert list(out.columns) == ["inference_result"] and out["inference_result"][1] == [0, 1, 0, 0]
