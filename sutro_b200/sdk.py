@@ -153,8 +153,10 @@ class Sutro(Templates, BaseSutroClient):
         job.stats = res.stats
         job.cum_logprobs = getattr(res, "cum_logprobs", None)
         if res.embeddings is not None:
+            # one fp32 [n_rows, d] array; the per-row "outputs" are views into it (a million
+            # rows must not become a billion Python floats)
             job.embeddings = res.embeddings
-            job.outputs = [row.tolist() for row in res.embeddings]
+            job.outputs = list(res.embeddings)
         else:
             job.outputs = res.outputs
         job.status = JobStatus.SUCCEEDED
@@ -298,7 +300,17 @@ class Sutro(Templates, BaseSutroClient):
         if not disable_cache:
             try:
                 os.makedirs(self.cache_dir, exist_ok=True)
-                df.to_parquet(path, compression="snappy")
+                if j.embeddings is not None:
+                    import pyarrow as pa
+                    import pyarrow.parquet as pq
+                    emb = j.embeddings
+                    vec = pa.FixedSizeListArray.from_arrays(pa.array(emb.reshape(-1)), emb.shape[1])
+                    names, arrays = [output_column], [vec]
+                    if include_inputs:
+                        names, arrays = ["inputs"] + names, [pa.array(j.inputs)] + arrays
+                    pq.write_table(pa.table(arrays, names=names), path, compression="snappy")
+                else:
+                    df.to_parquet(path, compression="snappy")
             except Exception as e:  # cache is best effort
                 self._say(f"(results cache not written: {e})")
         if unpack_json and len(df) and isinstance(df[output_column].iloc[0], str):

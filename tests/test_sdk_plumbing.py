@@ -252,4 +252,10 @@ def test_embed_returns_vector_column():
             return GenerationResult(None, None, np.eye(len(rows), 4, dtype=np.float32), {})
     c.register_engine("qwen-3-embedding-0.6b", Emb())
     out = c.embed(["a", "b"])
-    assert list(out.columns) == ["inference_result"] and out["inference_result"][1] == [0, 1, 0, 0]
+    assert list(out.columns) == ["inference_result"]
+    assert out["inference_result"][1].tolist() == [0, 1, 0, 0]
+    import pyarrow.parquet as pq
+    jid = c.list_jobs()[-1]["job_id"]
+    t = pq.read_table(f"/tmp/sb200-test-cache/{jid}.snappy.parquet")
+    assert t.column("inference_result").to_pylist()[1] == [0.0, 1.0, 0.0, 0.0]
+    assert c.get_job_embeddings(jid).shape == (2, 4)
