@@ -22,6 +22,7 @@ constexpr int kPfWarps = 8;
 constexpr int kPfStages = 3;                    // ring of 32-token super-tiles (2 pages)
 constexpr int kPfStageBytes = 4 * kTileBytes;   // K0 | V0 | K1 | V1
 constexpr int kPfSmem = kPfStages * kPfStageBytes + 1024;
+constexpr int kPfMaxPages = 1024;               // 16 k tokens of context per sequence
 
 template <int G>
 __global__ void __launch_bounds__(kPfWarps * 32, 2)
@@ -36,6 +37,9 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
   __shared__ uint64_t full_bar[kPfStages];
+  // page ids of this sequence, staged once: the producer lane must not sit on a dependent
+  // global load (page table -> bulk copy) in every iteration while 7 warps wait at the barrier
+  __shared__ int32_t s_pt[kPfMaxPages];
 
   const int seq = work[2 * blockIdx.x];
   const int qt0 = work[2 * blockIdx.x + 1];
@@ -63,6 +67,7 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     for (int s = 0; s < kPfStages; ++s) mbar_init(smem_u32(&full_bar[s]), 1);
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < n_pages; i += kPfWarps * 32) s_pt[i] = pt[i];
   __syncthreads();
 
   // one super-tile = up to two pages, each one flat 8 KiB copy (K tile + V tile)
@@ -72,11 +77,11 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     const uint32_t bar = smem_u32(&full_bar[stage]);
     const uint32_t dst = smem_u32(smem + stage * kPfStageBytes);
     mbar_arrive_expect_tx(bar, two ? 4 * kTileBytes : 2 * kTileBytes);
-    bulk_load_1d(dst, kv_layer + (static_cast<size_t>(pt[p0]) * hkv + kvh) * (2 * kTileElems),
+    bulk_load_1d(dst, kv_layer + (static_cast<size_t>(s_pt[p0]) * hkv + kvh) * (2 * kTileElems),
                  2 * kTileBytes, bar);
     if (two)
       bulk_load_1d(dst + 2 * kTileBytes,
-                   kv_layer + (static_cast<size_t>(pt[p0 + 1]) * hkv + kvh) * (2 * kTileElems),
+                   kv_layer + (static_cast<size_t>(s_pt[p0 + 1]) * hkv + kvh) * (2 * kTileElems),
                    2 * kTileBytes, bar);
   };
   if (threadIdx.x == 0) {
@@ -264,6 +269,11 @@ int attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t
   if (n_work <= 0) return 0;
   if (hkv <= 0 || hq % hkv != 0) {
     set_last_error("attn_prefill: hq=%d not a multiple of hkv=%d", hq, hkv);
+    return -1;
+  }
+  if (max_pages > kPfMaxPages) {
+    set_last_error("attn_prefill: max_pages=%d exceeds the staged page-table size %d", max_pages,
+                   kPfMaxPages);
     return -1;
   }
 #define SB_PF(G)                                                                               \
