@@ -362,12 +362,7 @@ int launch(const void* qkv, void* out, const void* kv_layer, const int32_t* page
            int max_pages, const int32_t* row_slot, const int32_t* ctx_len, int B, int hq, int hkv,
            float scale, cudaStream_t stream) {
   auto kern = attn_decode_kernel<G>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA_CHECK(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmem));
-    attr_set = true;
-  }
+  SB_SET_MAX_SMEM(kern, kDecSmem);
   const int n_pairs = B * hkv;
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
@@ -375,12 +370,7 @@ int launch(const void* qkv, void* out, const void* kv_layer, const int32_t* page
   // enough pairs to give every resident warp (2 CTAs x 4 warps per SM) a few of its own
   if ((n_pairs >= sms * 2 * kDecWarps * 2 && !g_force_split) || g_force_warp) {
     auto wk = attn_decode_warp_kernel<G>;
-    static bool wattr = false;
-    if (!wattr) {
-      SB_CUDA_CHECK(
-          cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmem));
-      wattr = true;
-    }
+    SB_SET_MAX_SMEM(wk, kDecSmem);
     wk<<<(n_pairs + kDecWarps - 1) / kDecWarps, kDecWarps * 32, kDecSmem, stream>>>(
         static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
         static_cast<const __nv_bfloat16*>(kv_layer), page_table, max_pages, row_slot, ctx_len,

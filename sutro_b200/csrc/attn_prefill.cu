@@ -244,11 +244,7 @@ int launch(const void* qkv, void* out, const void* kv_layer, const int32_t* page
            const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past, int hq,
            int hkv, float scale, cudaStream_t stream) {
   auto kern = attn_prefill_kernel<G>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmem));
-    attr_set = true;
-  }
+  SB_SET_MAX_SMEM(kern, kPfSmem);
   dim3 grid(n_work, hkv);
   kern<<<grid, kPfWarps * 32, kPfSmem, stream>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),

@@ -30,6 +30,31 @@ void set_last_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
+// cudaFuncSetAttribute is per device: remember, per call site, on which devices the
+// dynamic-shared-memory limit has already been raised (one engine per GPU may live in the
+// same process, each driven from its own host thread).
+struct PerDeviceOnce {
+  unsigned long long done = 0;  // bit d == device d configured (<= 64 devices)
+  bool need(int& dev) {
+    dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 || dev >= 64 || !((__atomic_load_n(&done, __ATOMIC_ACQUIRE) >> dev) & 1ull);
+  }
+  void mark(int dev) {
+    if (dev >= 0 && dev < 64) __atomic_fetch_or(&done, 1ull << dev, __ATOMIC_RELEASE);
+  }
+};
+#define SB_SET_MAX_SMEM(kernel, bytes)                                                        \
+  do {                                                                                        \
+    static ::sb::PerDeviceOnce _once;                                                         \
+    int _dev;                                                                                 \
+    if (_once.need(_dev)) {                                                                   \
+      SB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         bytes));                                             \
+      _once.mark(_dev);                                                                       \
+    }                                                                                         \
+  } while (0)
+
 // ---------------------------------------------------------------------------
 // misc
 // ---------------------------------------------------------------------------

@@ -671,14 +671,16 @@ int make_tmap(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* ou
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cached[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cached[dev];
 }
 
 // Row-tiles per raster group: as many as keep the group's A slab (rows x K bf16) within
@@ -699,12 +701,7 @@ int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* re
   if (make_tmap(a, a_rows, K, kBlockM, &tm_a)) return -1;
   if (make_tmap(w, N, K, BLOCK_N, &tm_b)) return -1;
   auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  SB_SET_MAX_SMEM(kern, Cfg::kSmemBytes);
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, gemm_threads<EPI>(), Cfg::kSmemBytes, stream>>>(
@@ -721,12 +718,7 @@ int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* r
   if (make_tmap(a, a_rows, K, 128, &tm_a)) return -1;
   if (make_tmap(w, N, K, 128, &tm_b)) return -1;
   auto kern = gemm2_bf16_tn_kernel<EPI, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       k2SmemBytes(STAGES)));
-    attr_set = true;
-  }
+  SB_SET_MAX_SMEM(kern, k2SmemBytes(STAGES));
   const int tiles = ((M + 255) / 256) * ((N + k2BlockN - 1) / k2BlockN);
   const int clusters = std::min(tiles, num_sms() / 2);
   kern<<<2 * clusters, gemm_threads<EPI>(), k2SmemBytes(STAGES), stream>>>(

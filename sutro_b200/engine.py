@@ -498,3 +498,84 @@ class LocalEngine:
         return GenerationResult(outputs, out_tokens, emb, stats,
                                 None if d_first is None else d_first.cpu(),
                                 None if d_lp is None else d_lp.cpu().numpy())
+
+
+# --------------------------------------------------------------------------- several GPUs, one process
+class MultiGpuEngine:
+    """Row-sharded replicas inside one process: one LocalEngine per device, each driven from
+    its own host thread (the C-ABI calls release the GIL).  Rows are split into contiguous
+    blocks, results are concatenated in order — the path has no exchange step, so there is no
+    data-path collective.  Weights are drawn once on the first device and broadcast to the
+    others (`torch.cuda.comm.broadcast`: NCCL over NVLink when available)."""
+
+    def __init__(self, engines: List[LocalEngine]):
+        if not engines:
+            raise ValueError("MultiGpuEngine needs at least one engine")
+        self.engines = engines
+        self.spec, self.vocab = engines[0].spec, engines[0].vocab
+        self.tokenizer = engines[0].tokenizer
+
+    @classmethod
+    def from_seed(cls, model: str, devices: Sequence[int], seed: int = 0, vocab_seed: int = 0, **kw):
+        spec = MS.get_spec(model)
+        devs = [torch.device("cuda", d) for d in devices]
+        if spec.n_params() > 50_000_000:
+            w0 = MS.make_engine_weights_on_device(spec, seed, devs[0])
+        else:
+            w0 = MS.pack_for_engine(spec, MS.make_weights(spec, seed), devs[0])
+        v = VB.build_vocab(spec.family, spec.vocab_size, seed=vocab_seed)
+        replicas = [w0] + [cls._replicate(spec, w0, d) for d in devs[1:]]
+        return cls([LocalEngine(spec, w, v, device=d, **kw) for w, d in zip(replicas, devs)])
+
+    @staticmethod
+    def _replicate(spec, w0: MS.EngineWeights, dev) -> MS.EngineWeights:
+        import torch.cuda.comm as comm
+
+        def cp(t):
+            return None if t is None else comm.broadcast(t, [t.device.index, dev.index])[1]
+        embed = cp(w0.embed)
+        lm = embed if spec.tied_embeddings else cp(w0.lm_head)
+        out = MS.EngineWeights(embed=embed, lm_head=lm, final_norm=cp(w0.final_norm))
+        for name in ("ln1", "ln2", "wqkv", "wo", "wgu", "wd", "q_norm", "k_norm"):
+            setattr(out, name, [cp(t) for t in getattr(w0, name)])
+        return out
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def generate(self, rows, **kw) -> GenerationResult:
+        from concurrent.futures import ThreadPoolExecutor
+
+        from .sharding import shard_bounds
+        if kw.get("progress") is not None:
+            kw = dict(kw, progress=None)   # per-shard progress callbacks are not merged
+        rows = list(rows) if not isinstance(rows, list) else rows
+        n, g = len(rows), len(self.engines)
+        spans = [shard_bounds(n, g, r) for r in range(g)]
+        work = [(e, rows[lo:hi]) for e, (lo, hi) in zip(self.engines, spans) if hi > lo]
+        if not work:
+            return self.engines[0].generate(rows, **kw)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=len(work)) as pool:
+            parts = list(pool.map(lambda a: a[0].generate(a[1], **kw), work))
+        return self._merge(parts, time.perf_counter() - t0)
+
+    @staticmethod
+    def _merge(parts: List[GenerationResult], wall_s: float) -> GenerationResult:
+        def cat(name):
+            vals = [getattr(p, name) for p in parts]
+            if any(v is None for v in vals):
+                return None
+            if isinstance(vals[0], np.ndarray):
+                return np.concatenate(vals, axis=0)
+            if torch.is_tensor(vals[0]):
+                return torch.cat(vals, dim=0)
+            return [x for v in vals for x in v]
+        stats: Dict[str, Any] = {"n_gpus": len(parts), "t_total_s": wall_s,
+                                 "per_gpu": [p.stats for p in parts]}
+        for k in ("n_rows", "input_tokens", "output_tokens", "decode_tokens", "prefill_tokens",
+                  "rows_done", "rows_truncated", "h2d_bytes", "d2h_bytes"):
+            stats[k] = sum(int(p.stats.get(k, 0)) for p in parts)
+        return GenerationResult(cat("outputs"), cat("out_tokens"), cat("embeddings"), stats,
+                                cat("first_logits"), cat("cum_logprobs"))

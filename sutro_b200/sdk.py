@@ -72,12 +72,17 @@ class Sutro(Templates, BaseSutroClient):
 
     def _engine(self, model: str):
         if model not in self._engines:
-            from .engine import LocalEngine
-            self._say(f"Loading {model} on cuda:{self.devices[0]} (random-init weights, seed "
+            from .engine import LocalEngine, MultiGpuEngine
+            where = ", ".join(f"cuda:{d}" for d in self.devices)
+            self._say(f"Loading {model} on {where} (random-init weights, seed "
                       f"{self.weights_seed}: no checkpoints are available offline)")
-            self._engines[model] = LocalEngine.from_seed(model, seed=self.weights_seed,
-                                                         device=self.devices[0],
-                                                         **self.engine_options)
+            if len(self.devices) > 1:   # one replica per GPU, rows sharded across them
+                self._engines[model] = MultiGpuEngine.from_seed(
+                    model, self.devices, seed=self.weights_seed, **self.engine_options)
+            else:
+                self._engines[model] = LocalEngine.from_seed(model, seed=self.weights_seed,
+                                                             device=self.devices[0],
+                                                             **self.engine_options)
         return self._engines[model]
 
     def register_engine(self, model: str, engine) -> None:

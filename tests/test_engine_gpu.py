@@ -254,6 +254,26 @@ def test_sampling_edge_settings_and_seeding():
         Extract.model_validate(json.loads(o))
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_in_process_multi_gpu_matches_single_gpu():
+    """MultiGpuEngine: replicas on cuda:0 and cuda:1, rows sharded, outputs positional."""
+    from sutro_b200.engine import LocalEngine, MultiGpuEngine
+    spec = MS.get_spec("tiny-qwen3")
+    w = MS.make_weights(spec, seed=0, std=0.05)
+    v = VB.build_vocab(spec.family, spec.vocab_size, seed=0, n_trained=600)
+    e0 = LocalEngine(spec, MS.pack_for_engine(spec, w, "cuda:0"), v, device=0, kv_pages=256,
+                     max_slots=8, max_prefill_tokens=512)
+    w1 = MultiGpuEngine._replicate(spec, e0.weights, torch.device("cuda", 1))
+    e1 = LocalEngine(spec, w1, v, device=1, kv_pages=256, max_slots=8, max_prefill_tokens=512)
+    rows = synth.product_reviews(21, seed=4)
+    kw = dict(system_prompt=SYS, json_schema=SentimentEnum.model_json_schema(), max_new_tokens=32,
+              return_tokens=True)
+    single = e0.generate(rows, **kw)
+    multi = MultiGpuEngine([e0, e1]).generate(rows, **kw)
+    assert multi.stats["n_gpus"] == 2 and multi.stats["n_rows"] == 21
+    assert multi.outputs == single.outputs and multi.out_tokens == single.out_tokens
+
+
 def test_empty_and_null_inputs():
     spec, w, v, eng = build("tiny-qwen3", max_slots=4, max_prefill_tokens=256)
     assert eng.generate([], max_new_tokens=4).outputs == []
