@@ -27,6 +27,7 @@ import time
 import uuid
 from typing import Any, Dict, List, Optional, Type, Union
 
+import numpy as np
 import pandas as pd
 
 from .common import (ModelOptions, handle_data_helper, is_frame, normalize_output_schema, pl,
@@ -49,6 +50,7 @@ class _Job:
         self.stats: Dict[str, Any] = {}
         self.failure_reason: Optional[str] = None
         self.cum_logprobs = None
+        self.confidence = None
         self.created = time.time()
         self.cost_estimate: Optional[float] = None
 
@@ -157,6 +159,12 @@ class Sutro(Templates, BaseSutroClient):
         job.inputs = input_data
         job.stats = res.stats
         job.cum_logprobs = getattr(res, "cum_logprobs", None)
+        if json_schema is not None and job.cum_logprobs is not None:
+            # Schema-constrained job: the sampler's log-probabilities are taken over the
+            # schema-valid tokens only (forced tokens contribute 0), so exp(sum) is the
+            # probability of this output among all outputs the schema admits — for an enum
+            # field, the model's probability of the chosen label.
+            job.confidence = np.exp(np.asarray(job.cum_logprobs, dtype=np.float64))
         if res.embeddings is not None:
             # one fp32 [n_rows, d] array; the per-row "outputs" are views into it (a million
             # rows must not become a billion Python floats)
@@ -301,6 +309,8 @@ class Sutro(Templates, BaseSutroClient):
         cols[output_column] = j.outputs
         if include_cumulative_logprobs:
             cols["cumulative_logprobs"] = [float(x) for x in j.cum_logprobs]
+        if j.confidence is not None:   # kept whenever the job produced one (sdk.py:1122-1127)
+            cols["confidence_score"] = [float(x) for x in j.confidence]
         df = pd.DataFrame(cols)
         if not disable_cache:
             try:
@@ -330,7 +340,8 @@ class Sutro(Templates, BaseSutroClient):
                         for key in first["content"].keys():
                             df[key] = [d["content"].get(key) for d in decoded]
                         df = df.drop(columns=["content"])
-                    df = df.drop(columns=[output_column])
+                    if output_column not in first:   # a key may reuse the column's name (rank)
+                        df = df.drop(columns=[output_column])
             except Exception:
                 pass  # first row is not JSON: leave the column as text (sdk.py:1168-1170)
         if with_original_df is not None:

@@ -192,6 +192,8 @@ class SchemaEcho:
             for k, sch in props.items():
                 if "enum" in sch:
                     obj[k] = sch["enum"][i % len(sch["enum"])]
+                elif sch.get("type") == "array":
+                    obj[k] = list(sch["items"]["enum"])[: sch["minItems"]]
                 elif sch.get("type") == "integer":
                     obj[k] = sch["minimum"] + i % (sch["maximum"] - sch["minimum"] + 1)
                 else:
@@ -259,3 +261,82 @@ def test_embed_returns_vector_column():
     t = pq.read_table(f"/tmp/sb200-test-cache/{jid}.snappy.parquet")
     assert t.column("inference_result").to_pylist()[1] == [0.0, 1.0, 0.0, 0.0]
     assert c.get_job_embeddings(jid).shape == (2, 4)
+
+
+def test_rank_returns_permutations_and_prints_elo(capsys):
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+    eng = SchemaEcho()
+    c.register_engine("m", eng)
+    assert list(inspect.signature(Sutro.rank).parameters) == [
+        "self", "model", "job_priority", "name", "description", "data", "option_labels",
+        "criteria", "ranking_column_name", "run_elo"]            # sutro/templates/evals.py:78-93
+    assert list(inspect.signature(Sutro.elo).parameters) == [
+        "data", "column", "laplace", "max_iter", "tol", "elo_mean"]
+    rows = [["short", "long", "mid"], ["x", None, "z"], ["1", "2", "3"], ["q", "r", "s"]]
+    out = c.rank(model="m", data=rows, option_labels=["A", "B", "C"], criteria="brevity")
+    assert list(out.columns) == ["A", "B", "C", "ranking"]
+    assert all(sorted(r) == ["A", "B", "C"] for r in out["ranking"])
+    sent, kw = eng.calls[0]
+    assert sent[0] == "A: short B: long C: mid" and sent[1] == "A: x B:  C: z"
+    perms = kw["json_schema"]["properties"]["ranking"]["enum"]
+    assert len(perms) == 6 and ["B", "A", "C"] in perms
+    assert "brevity" in kw["system_prompt"]
+    assert "elo" in capsys.readouterr().out
+    # pandas frame in -> pandas frame out with the ranking appended; input not mutated
+    df = pd.DataFrame({"A": ["a1", "a2"], "B": ["b1", "b2"], "other": [1, 2]})
+    out2 = c.rank(model="m", data=df, option_labels=["B", "A"], criteria=["c1", "c2"],
+                  ranking_column_name="order", run_elo=False)
+    assert list(out2.columns) == ["A", "B", "other", "order"] and "order" not in df.columns
+    assert eng.calls[-1][0][0] == "B: b1 A: a1"
+    # more than six labels: array-of-enum schema with a fixed length
+    labels = [f"L{i}" for i in range(7)]
+    c.rank(model="m", data=[[str(i) for i in range(7)]], option_labels=labels, criteria="x",
+           run_elo=False)
+    assert eng.calls[-1][1]["json_schema"]["properties"]["ranking"]["minItems"] == 7
+    with pytest.raises(ValueError):
+        c.rank(model="m", data=[["only-one"]], option_labels=["A", "B"], criteria="x")
+    with pytest.raises(ValueError):
+        c.rank(model="m", data=df, option_labels=["A", "missing"], criteria="x")
+    with pytest.raises(ValueError):
+        c.rank(model="m", data=df, option_labels=["A", "A"], criteria="x")
+
+
+def test_rank_schemas_compile_to_permutation_dfas():
+    """The rank schemas are inside the FSM compiler's subset; the small-n one admits exactly
+    the permutations."""
+    import itertools
+    from sutro_b200.schema_fsm import compile_schema
+    labels = ["A", "B", "C"]
+    sch = {"type": "object", "properties": {"ranking": {"enum": [list(p) for p in
+                                                                  itertools.permutations(labels)]}},
+           "required": ["ranking"]}
+    dfa = compile_schema(sch)
+    assert dfa.matches(b'{"ranking":["B","A","C"]}')
+    assert not dfa.matches(b'{"ranking":["B","B","C"]}')
+    assert not dfa.matches(b'{"ranking":["B","A"]}')
+    big = [f"L{i}" for i in range(7)]
+    sch7 = {"type": "object", "properties": {"ranking": {"type": "array", "items": {
+        "type": "string", "enum": big}, "minItems": 7, "maxItems": 7}}, "required": ["ranking"]}
+    dfa7 = compile_schema(sch7)
+    assert dfa7.matches(('{"ranking":' + json.dumps(big, separators=(",", ":")) + "}").encode())
+    assert not dfa7.matches(('{"ranking":' + json.dumps(big[:6], separators=(",", ":")) + "}").encode())
+
+
+def test_confidence_score_column_for_schema_jobs():
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+
+    class E:
+        def generate(self, rows, **kw):
+            outs = [json.dumps({"sentiment": "pos"}) for _ in rows]
+            return GenerationResult(outs, None, None, {}, None,
+                                    np.log(np.array([0.5, 0.25], dtype=np.float32)))
+    c.register_engine("qwen-3-4b", E())
+    jid = c.infer(["a", "b"], model="qwen-3-4b", output_schema=Sentiment, stay_attached=False)
+    df = c.get_job_results(jid, include_cumulative_logprobs=True)
+    assert list(df.columns) == ["cumulative_logprobs", "confidence_score", "sentiment"]
+    assert np.allclose(df["confidence_score"], [0.5, 0.25])
+    raw = c.get_job_results(jid, unpack_json=False)
+    assert list(raw.columns) == ["inference_result", "confidence_score"]
+    # no schema -> no confidence column (only cumulative logprobs on request)
+    jid2 = c.infer(["a", "b"], model="qwen-3-4b", stay_attached=False)
+    assert list(c.get_job_results(jid2, unpack_json=False).columns) == ["inference_result"]
