@@ -195,6 +195,10 @@ typedef struct {
   int seed_per_row;               /* 1: every row draws from its own Philox stream       */
   float* out_cum_logprob_dev;     /* optional [n_rows]: sum of log p(token) under the masked
                                      softmax at the sampling temperature; NULL = off      */
+  const int64_t* row_ids_dev;     /* optional device [n_rows]: the id that keys a row's Philox
+                                     stream when seed_per_row = 1 (the row's index in the whole
+                                     job when the job is sharded over GPUs, so that draws do not
+                                     depend on the sharding); NULL = the local row index       */
 } sb200_job;
 
 /* kernel classes for the per-class launch counts / device times in sb200_job_stats */

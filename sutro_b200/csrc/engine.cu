@@ -389,6 +389,7 @@ struct Engine {
       a.top_p = (job.top_p > 0.f && job.top_p < 1.f) ? job.top_p : 1.f;
       a.seed = job.seed;
       a.seed_per_row = job.seed_per_row;
+      a.row_ids = job.row_ids_dev;
       a.slot_cum_logprob = job.out_cum_logprob_dev ? slot_cum_logprob : nullptr;
       a.out_cum_logprob = job.out_cum_logprob_dev;
       SB_K(SB200_KC_SAMPLE, sample_greedy(a, stream));

@@ -122,6 +122,7 @@ struct SampleArgs {
   float top_p;             // >= 1: off
   uint64_t seed;
   int seed_per_row;        // random_seed_per_input (sutro/sdk.py:204): 1 = own stream per row
+  const int64_t* row_ids;  // optional [n_rows]: stream id per row (null = row index)
   float* slot_cum_logprob; // nullable: running sum of log p(token) under the masked softmax
   float* out_cum_logprob;  // [n_rows], written together with out_len
 };

@@ -319,7 +319,9 @@ __global__ void __launch_bounds__(kSampleThreads) sample_random_kernel(SampleArg
   __syncthreads();
   const float total = wsum[kSampleWarps];
   const int row = a.slot_row[slot];
-  const uint64_t ctr_row = a.seed_per_row ? static_cast<uint64_t>(row) : 0ull;
+  const uint64_t row_id =
+      a.row_ids != nullptr ? static_cast<uint64_t>(a.row_ids[row]) : static_cast<uint64_t>(row);
+  const uint64_t ctr_row = a.seed_per_row ? row_id : 0ull;
   const uint4 rnd = philox4x32_10(
       make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32)),
       make_uint4(static_cast<uint32_t>(ctr_row), static_cast<uint32_t>(ctr_row >> 32),

@@ -62,7 +62,7 @@ class JobC(C.Structure):
                 ("out_first_logits_dev", C.c_void_p),
                 ("temperature", C.c_float), ("top_k", C.c_int), ("top_p", C.c_float),
                 ("seed", C.c_uint64), ("seed_per_row", C.c_int),
-                ("out_cum_logprob_dev", C.c_void_p)]
+                ("out_cum_logprob_dev", C.c_void_p), ("row_ids_dev", C.c_void_p)]
 
 
 KERNEL_CLASSES = ["gemm", "attn_decode", "attn_prefill", "norm", "rope", "sample", "embed",
@@ -356,7 +356,8 @@ class LocalEngine:
                  profile: bool = False, return_first_logits: bool = False,
                  jump_forward: bool = True, temperature: float = 0.0, top_k: int = 0,
                  top_p: float = 1.0, seed: int = 0, seed_per_row: bool = False,
-                 return_logprobs: bool = False) -> GenerationResult:
+                 return_logprobs: bool = False,
+                 row_ids: Optional[Sequence[int]] = None) -> GenerationResult:
         """The whole hot path for one frame column.  Three phases, timed separately:
           A  host -> HBM   : rows -> Arrow blob, template/schema compile (cached), H2D copy
           B  device        : tokenize, prefill/decode (+mask), detokenize — HBM to HBM
@@ -435,6 +436,14 @@ class LocalEngine:
                 job.out_first_logits_dev = d_first.data_ptr()
             job.temperature, job.top_k, job.top_p = float(temperature), int(top_k), float(top_p)
             job.seed, job.seed_per_row = int(seed) & (2 ** 64 - 1), int(seed_per_row)
+            d_ids = None
+            if row_ids is not None and seed_per_row:
+                # rows of a sharded job keep the Philox stream of their index in the whole job
+                ids = np.ascontiguousarray(row_ids, dtype=np.int64)
+                if ids.shape != (n_rows,):
+                    raise ValueError("row_ids must hold one id per row")
+                d_ids = torch.from_numpy(ids).to(dev)
+                job.row_ids_dev = d_ids.data_ptr()
             d_lp = None
             if return_logprobs and not emb_mode:
                 d_lp = torch.zeros(n_rows, dtype=torch.float32, device=dev)
@@ -544,38 +553,61 @@ class MultiGpuEngine:
         for e in self.engines:
             e.close()
 
-    def generate(self, rows, **kw) -> GenerationResult:
+    def generate(self, rows, balance: str = "bytes", **kw) -> GenerationResult:
+        """Same arguments as `LocalEngine.generate`.  `balance="bytes"` deals rows to the GPUs
+        longest-first (`sharding.balanced_shards`, byte length as the proxy for tokens);
+        `"rows"` uses contiguous blocks.  Either way row i of the result belongs to row i of
+        the input, and per-row random streams are keyed by the row's index in the whole job,
+        so the outputs do not depend on how many GPUs shared the work."""
         from concurrent.futures import ThreadPoolExecutor
 
-        from .sharding import shard_bounds
+        from .sharding import balanced_shards, shard_bounds
         if kw.get("progress") is not None:
             kw = dict(kw, progress=None)   # per-shard progress callbacks are not merged
-        rows = list(rows) if not isinstance(rows, list) else rows
+        rows = rows if isinstance(rows, list) else list(rows)
         n, g = len(rows), len(self.engines)
-        spans = [shard_bounds(n, g, r) for r in range(g)]
-        work = [(e, rows[lo:hi]) for e, (lo, hi) in zip(self.engines, spans) if hi > lo]
+        if balance == "rows":
+            shards = [list(range(*shard_bounds(n, g, r))) for r in range(g)]
+        elif balance == "bytes":
+            shards = balanced_shards([0 if r is None else len(str(r).encode("utf-8"))
+                                      for r in rows], g)
+        else:
+            raise ValueError("balance must be 'rows' or 'bytes'")
+        work = [(e, idx) for e, idx in zip(self.engines, shards) if idx]
         if not work:
             return self.engines[0].generate(rows, **kw)
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=len(work)) as pool:
-            parts = list(pool.map(lambda a: a[0].generate(a[1], **kw), work))
-        return self._merge(parts, time.perf_counter() - t0)
+            parts = list(pool.map(
+                lambda a: a[0].generate([rows[i] for i in a[1]], row_ids=a[1], **kw), work))
+        return self._merge(parts, [idx for _, idx in work], n, time.perf_counter() - t0)
 
     @staticmethod
-    def _merge(parts: List[GenerationResult], wall_s: float) -> GenerationResult:
-        def cat(name):
+    def _merge(parts: List[GenerationResult], shards: List[List[int]], n_rows: int,
+               wall_s: float) -> GenerationResult:
+        def scatter(name):
             vals = [getattr(p, name) for p in parts]
             if any(v is None for v in vals):
                 return None
             if isinstance(vals[0], np.ndarray):
-                return np.concatenate(vals, axis=0)
+                out = np.empty((n_rows,) + vals[0].shape[1:], dtype=vals[0].dtype)
+                for idx, v in zip(shards, vals):
+                    out[idx] = v
+                return out
             if torch.is_tensor(vals[0]):
-                return torch.cat(vals, dim=0)
-            return [x for v in vals for x in v]
+                out = torch.empty((n_rows,) + tuple(vals[0].shape[1:]), dtype=vals[0].dtype)
+                for idx, v in zip(shards, vals):
+                    out[torch.as_tensor(idx, dtype=torch.long)] = v
+                return out
+            out = [None] * n_rows
+            for idx, v in zip(shards, vals):
+                for i, x in zip(idx, v):
+                    out[i] = x
+            return out
         stats: Dict[str, Any] = {"n_gpus": len(parts), "t_total_s": wall_s,
                                  "per_gpu": [p.stats for p in parts]}
         for k in ("n_rows", "input_tokens", "output_tokens", "decode_tokens", "prefill_tokens",
                   "rows_done", "rows_truncated", "h2d_bytes", "d2h_bytes"):
             stats[k] = sum(int(p.stats.get(k, 0)) for p in parts)
-        return GenerationResult(cat("outputs"), cat("out_tokens"), cat("embeddings"), stats,
-                                cat("first_logits"), cat("cum_logprobs"))
+        return GenerationResult(scatter("outputs"), scatter("out_tokens"), scatter("embeddings"),
+                                stats, scatter("first_logits"), scatter("cum_logprobs"))

@@ -272,6 +272,29 @@ def test_in_process_multi_gpu_matches_single_gpu():
     multi = MultiGpuEngine([e0, e1]).generate(rows, **kw)
     assert multi.stats["n_gpus"] == 2 and multi.stats["n_rows"] == 21
     assert multi.outputs == single.outputs and multi.out_tokens == single.out_tokens
+    # sampled decoding with per-row streams: the draws follow the row's index in the whole job
+    skw = dict(system_prompt=SYS, max_new_tokens=12, return_tokens=True, temperature=0.9,
+               top_k=20, seed=5, seed_per_row=True, return_logprobs=True)
+    s1 = e0.generate(rows, **skw)
+    for balance in ("bytes", "rows"):
+        s2 = MultiGpuEngine([e0, e1]).generate(rows, balance=balance, **skw)
+        assert s2.out_tokens == s1.out_tokens
+        assert np.allclose(s2.cum_logprobs, s1.cum_logprobs, atol=1e-3)
+
+
+def test_row_ids_key_the_per_row_random_streams():
+    """A shard that passes the rows' job-wide indices draws what the unsharded job draws."""
+    spec, w, v, eng = build("tiny-qwen3", max_slots=16, max_prefill_tokens=1024)
+    rows = synth.product_reviews(12, seed=9)
+    kw = dict(system_prompt=SYS, max_new_tokens=10, return_tokens=True, temperature=1.0,
+              seed=3, seed_per_row=True)
+    whole = eng.generate(rows, **kw)
+    part = eng.generate(rows[5:], row_ids=list(range(5, 12)), **kw)
+    assert part.out_tokens == whole.out_tokens[5:]
+    local = eng.generate(rows[5:], **kw)                     # local indices: other streams
+    assert local.out_tokens != whole.out_tokens[5:]
+    with pytest.raises(ValueError):
+        eng.generate(rows[5:], row_ids=[1, 2], **kw)
 
 
 def test_empty_and_null_inputs():

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sutro_b200.sharding import broadcast_weights, infer_sharded, shard_bounds
+from sutro_b200.sharding import balanced_shards, broadcast_weights, infer_sharded, shard_bounds
 
 
 def test_shard_bounds_cover_every_row_once():
@@ -21,10 +21,64 @@ def test_shard_bounds_cover_every_row_once():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_balanced_shards_partition_rows_and_even_out_cost():
+    import random
+    rng = random.Random(0)
+    costs = [int(rng.lognormvariate(4.5, 0.6)) for _ in range(20001)]
+    for world in (1, 2, 3, 8):
+        shards = balanced_shards(costs, world)
+        assert sorted(i for s in shards for i in s) == list(range(len(costs)))
+        assert all(s == sorted(s) for s in shards)
+        sizes = [len(s) for s in shards]
+        loads = [sum(costs[i] for i in s) for s in shards]
+        assert max(sizes) - min(sizes) <= 1
+        assert max(loads) - min(loads) <= max(costs)          # within one row of each other
+    # contiguous blocks of length-sorted data are badly unbalanced; the snake deal is not
+    ordered = sorted(costs)
+    blocks = [sum(ordered[slice(*shard_bounds(len(ordered), 4, r))]) for r in range(4)]
+    dealt = [sum(ordered[i] for i in s) for s in balanced_shards(ordered, 4)]
+    assert max(blocks) > 2 * min(blocks) and max(dealt) - min(dealt) <= max(ordered)
+    assert balanced_shards([], 2) == [[], []] and balanced_shards([7], 3) == [[0], [], []]
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def _worker_balanced(rank, world, port, n_rows, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rows = [("x" * ((i * 7) % 13)) + f"|{i}" for i in range(n_rows)] + [None]
+        out = infer_sharded(rows, lambda shard: [f"{r}@{rank}" for r in shard], dst=0,
+                            balance="bytes")
+        if rank == 0:
+            q.put(out)
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_infer_sharded_balanced_scatter_back_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n_rows = 23
+    procs = [ctx.Process(target=_worker_balanced, args=(r, 2, port, n_rows, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    rows = [("x" * ((i * 7) % 13)) + f"|{i}" for i in range(n_rows)] + [None]
+    shards = balanced_shards([0 if r is None else len(r) for r in rows], 2)
+    owner = {i: r for r, s in enumerate(shards) for i in s}
+    assert out == [f"{rows[i]}@{owner[i]}" for i in range(len(rows))]
+    assert {owner[i] for i in range(len(rows))} == {0, 1}
 
 
 def _worker(rank, world, port, n_rows, q):
