@@ -200,6 +200,29 @@ def cpu_baseline(spec, hf_weights, vocab, rows, threads: int, budget_s: float = 
             "output_tokens_per_s": n_out / dt}
 
 
+def plumbing_cost(model, rows, outputs):
+    """the only code of this path the reference runs locally is the host
+    plumbing — column extraction (sutro/common.py:111-149), payload build + JSON encode
+    (sutro/sdk.py:196-208) and positional write-back (:408-412).  Timed here through this
+    repo's restatement (sutro_b200.common; pinned to the reference by tests/golden/
+    plumbing.json) on the benchmark's own rows, single thread."""
+    import pandas as pd
+    from sutro_b200.common import handle_data_helper
+    df = pd.DataFrame({"review_text": rows})
+    t0 = time.perf_counter()
+    inputs = handle_data_helper(df, "review_text")
+    payload = {"model": model, "inputs": inputs, "job_priority": 0, "json_schema": None,
+               "system_prompt": None, "cost_estimate": False, "sampling_params": None,
+               "random_seed_per_input": False, "truncate_rows": True, "name": None,
+               "description": None}
+    body = json.dumps(payload)
+    df["inference_result"] = outputs
+    dt = time.perf_counter() - t0
+    return {"rows_per_s": len(rows) / dt, "ms_total": 1e3 * dt, "payload_bytes": len(body),
+            "rows": len(rows), "cores": 1,
+            "what": "handle_data_helper + payload json + write-back (restated reference plumbing)"}
+
+
 def run_reference_arm(args):
     """`--impl reference`: there is no reference CPU code for this path (the reference
     POSTs to a hosted service), so this arm times the CPU oracle on the host cores."""
@@ -423,6 +446,12 @@ def main():
             cpu = {"value": None, "unit": "rows/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"failed: {e!r}"}
 
+    plumbing = None
+    if rank == 0:
+        try:
+            plumbing = plumbing_cost(args.model, shards[-1], results[-1].outputs)
+        except Exception as e:
+            plumbing = {"failed": repr(e)}
     if rank == 0:
         st = results[-1].stats
         line = {
@@ -441,7 +470,7 @@ def main():
             "gpu_launches": int(launches_all),
             "roofline": roofline, "roofline_attn_decode": roofline_attn,
             "kernel_ms_profiled_step": kms,
-            "cpu_baseline": cpu, "clocks": clk,
+            "cpu_baseline": cpu, "host_plumbing": plumbing, "clocks": clk,
             "outputs_valid": bool(ok),
             "job": {k: st[k] for k in ("prefill_steps", "decode_steps", "prefix_cached_tokens",
                                        "input_tokens", "output_tokens", "decode_tokens",

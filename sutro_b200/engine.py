@@ -562,8 +562,7 @@ class MultiGpuEngine:
         from concurrent.futures import ThreadPoolExecutor
 
         from .sharding import balanced_shards, shard_bounds
-        if kw.get("progress") is not None:
-            kw = dict(kw, progress=None)   # per-shard progress callbacks are not merged
+        progress = kw.pop("progress", None)
         rows = rows if isinstance(rows, list) else list(rows)
         n, g = len(rows), len(self.engines)
         if balance == "rows":
@@ -575,11 +574,26 @@ class MultiGpuEngine:
             raise ValueError("balance must be 'rows' or 'bytes'")
         work = [(e, idx) for e, idx in zip(self.engines, shards) if idx]
         if not work:
-            return self.engines[0].generate(rows, **kw)
+            return self.engines[0].generate(rows, progress=progress, **kw)
+
+        def shard_progress(k):
+            # every shard reports its own running totals; the caller sees their sum
+            if progress is None:
+                return None
+
+            def cb(rows_done, in_tok, out_tok):
+                with lock:
+                    seen[k] = (rows_done, in_tok, out_tok)
+                    progress(*(sum(s[j] for s in seen) for j in range(3)))
+            return cb
+        import threading
+        lock, seen = threading.Lock(), [(0, 0, 0)] * len(work)
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=len(work)) as pool:
             parts = list(pool.map(
-                lambda a: a[0].generate([rows[i] for i in a[1]], row_ids=a[1], **kw), work))
+                lambda a: a[1][0].generate([rows[i] for i in a[1][1]], row_ids=a[1][1],
+                                           progress=shard_progress(a[0]), **kw),
+                list(enumerate(work))))
         return self._merge(parts, [idx for _, idx in work], n, time.perf_counter() - t0)
 
     @staticmethod

@@ -51,15 +51,71 @@ class _Job:
         self.failure_reason: Optional[str] = None
         self.cum_logprobs = None
         self.confidence = None
+        self.progress: Dict[str, Any] = {}
         self.created = time.time()
         self.cost_estimate: Optional[float] = None
+
+
+class _ProgressStream:
+    """Turns the engine's (rows_done, input_tokens, output_tokens) callback into the records
+    the reference reads from `stream-job-progress/{id}` (sutro/sdk.py:331-358):
+    `{"update_type": "progress", "result": rows_done}` and `{"update_type": "tokens",
+    "result": {input_tokens, output_tokens, total_tokens_processed_per_second}}`.  Records
+    go to `sink` (the client's `on_progress` hook) and, when `bar` is set, drive a tqdm bar
+    with the reference's postfix text; counters are merged monotonically like the reference
+    does."""
+
+    def __init__(self, job: _Job, sink=None, bar: bool = False):
+        self.job, self.sink = job, sink
+        self.t0 = time.perf_counter()
+        self.state = {"input_tokens": 0, "output_tokens": 0, "total_tokens_processed_per_second": 0}
+        self.rows = 0
+        self.pbar = None
+        if bar:
+            try:
+                from tqdm import tqdm
+                self.pbar = tqdm(total=job.n_rows, desc="Progress",
+                                 postfix="Input tokens processed: 0")
+            except Exception:
+                self.pbar = None
+
+    def __call__(self, rows_done: int, input_tokens: int, output_tokens: int) -> None:
+        dt = max(time.perf_counter() - self.t0, 1e-9)
+        records = [{"update_type": "progress", "result": int(rows_done)},
+                   {"update_type": "tokens",
+                    "result": {"input_tokens": int(input_tokens),
+                               "output_tokens": int(output_tokens),
+                               "total_tokens_processed_per_second":
+                                   round((input_tokens + output_tokens) / dt, 1)}}]
+        self.rows = max(self.rows, int(rows_done))
+        for k, v in records[1]["result"].items():
+            if k == "total_tokens_processed_per_second" or v >= self.state[k]:
+                self.state[k] = v
+        self.job.progress = {"rows_done": self.rows, **self.state}
+        if self.sink is not None:
+            for r in records:
+                self.sink(r)
+        if self.pbar is not None:
+            if self.rows > self.pbar.n:
+                self.pbar.update(self.rows - self.pbar.n)
+            self.pbar.postfix = (f"Input tokens processed: {self.state['input_tokens']}, Output "
+                                 f"tokens generated: {self.state['output_tokens']}, Total tokens/s: "
+                                 f"{self.state['total_tokens_processed_per_second']}")
+            self.pbar.refresh()
+
+    def close(self):
+        if self.pbar is not None:
+            self.pbar.close()
+            self.pbar = None
 
 
 class Sutro(Templates, BaseSutroClient):
     def __init__(self, devices: Optional[List[int]] = None, weights_seed: int = 0,
                  engine_options: Optional[Dict[str, Any]] = None, cache_dir: Optional[str] = None,
-                 verbose: bool = True):
+                 verbose: bool = True, on_progress=None):
         self.devices = devices or [0]
+        # optional callable(record): receives every progress / tokens record of a running job
+        self.on_progress = on_progress
         self.weights_seed = weights_seed
         self.engine_options = dict(engine_options or {})
         self.cache_dir = os.path.expanduser(cache_dir or "~/.sutro/job-results")
@@ -140,12 +196,18 @@ class Sutro(Templates, BaseSutroClient):
                           f"({job.stats['input_tokens']} input tokens)", "success")
                 return job.job_id
             t0 = time.perf_counter()
+            stream = None
+            if self.on_progress is not None or (stay_attached and self.verbose):
+                stream = _ProgressStream(job, self.on_progress,
+                                         bar=bool(stay_attached and self.verbose))
             res = eng.generate(input_data, system_prompt=system_prompt, json_schema=json_schema,
                                max_new_tokens=max_new, ignore_eos=bool(sp.get("ignore_eos", False)),
                                truncate_rows=truncate_rows, temperature=temperature, top_k=top_k,
                                top_p=top_p, seed=seed, seed_per_row=bool(random_seed_per_input),
-                               return_logprobs=True)
+                               return_logprobs=True, progress=stream)
             dt = time.perf_counter() - t0
+            if stream is not None:
+                stream.close()
         except KeyboardInterrupt:
             job.status = JobStatus.CANCELLED
             return None

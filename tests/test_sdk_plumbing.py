@@ -340,3 +340,58 @@ def test_confidence_score_column_for_schema_jobs():
     # no schema -> no confidence column (only cumulative logprobs on request)
     jid2 = c.infer(["a", "b"], model="qwen-3-4b", stay_attached=False)
     assert list(c.get_job_results(jid2, unpack_json=False).columns) == ["inference_result"]
+
+
+def test_progress_records_have_the_reference_stream_shape():     # sutro/sdk.py:331-358
+    seen = []
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache", on_progress=seen.append)
+
+    class E:
+        def generate(self, rows, progress=None, **kw):
+            progress(1, 40, 0)
+            progress(1, 30, 5)          # a stale input-token count must not move the state back
+            progress(len(rows), 80, 12)
+            return GenerationResult([f"o{i}" for i in range(len(rows))], None, None,
+                                    {"input_tokens": 80, "output_tokens": 12})
+    c.register_engine("qwen-3-4b", E())
+    jid = c.infer(["a", "b"], model="qwen-3-4b", stay_attached=False)
+    kinds = [r["update_type"] for r in seen]
+    assert kinds == ["progress", "tokens"] * 3
+    assert [r["result"] for r in seen if r["update_type"] == "progress"] == [1, 1, 2]
+    last = seen[-1]["result"]
+    assert set(last) == {"input_tokens", "output_tokens", "total_tokens_processed_per_second"}
+    assert (last["input_tokens"], last["output_tokens"]) == (80, 12)
+    st = c._job(jid).progress
+    assert st["rows_done"] == 2 and st["input_tokens"] == 80 and st["output_tokens"] == 12
+
+
+def test_multi_gpu_engine_merges_shard_progress_and_scatters_rows():
+    """MultiGpuEngine host logic with stub shards (no GPU): balanced assignment, job-wide
+    row ids, summed progress, positional scatter."""
+    from sutro_b200.engine import MultiGpuEngine
+
+    class Shard:
+        spec = vocab = tokenizer = None
+
+        def __init__(self, tag):
+            self.tag, self.got = tag, None
+
+        def generate(self, rows, row_ids=None, progress=None, **kw):
+            self.got = (list(rows), list(row_ids))
+            if progress:
+                progress(len(rows), 10 * len(rows), len(rows))
+            return GenerationResult([f"{r}@{self.tag}" for r in rows], [[i] for i in row_ids],
+                                    None, {"n_rows": len(rows), "output_tokens": len(rows)})
+    a, b = Shard("a"), Shard("b")
+    rows = ["x" * n for n in (9, 1, 5, 7, 3, 2)]
+    calls = []
+    res = MultiGpuEngine([a, b]).generate(rows, progress=lambda *t: calls.append(t))
+    assert [o.split("@")[0] for o in res.outputs] == rows                 # positional
+    assert res.out_tokens == [[i] for i in range(6)]                      # job-wide row ids
+    assert sorted(a.got[1] + b.got[1]) == list(range(6)) and len(a.got[1]) == len(b.got[1]) == 3
+    assert abs(sum(map(len, a.got[0])) - sum(map(len, b.got[0]))) <= 9
+    assert calls[-1] == (6, 60, 6) and res.stats["n_rows"] == 6
+    blocks = MultiGpuEngine([a, b]).generate(rows, balance="rows")
+    assert a.got[1] == [0, 1, 2] and b.got[1] == [3, 4, 5] and blocks.outputs[3] == "xxxxxxx@b"
+    with pytest.raises(ValueError):
+        MultiGpuEngine([a, b]).generate(rows, balance="tokens")
