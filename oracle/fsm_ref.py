@@ -5,7 +5,9 @@ forwards `json_schema`, sutro/sdk.py:199).  What "correct" means is therefore de
 the JSON-Schema semantics themselves: every string the automaton accepts must parse as
 JSON and validate against the schema (checked with pydantic / a small validator below),
 and every compact serialisation of a valid instance within the documented caps must be
-accepted.  TokenFSM is the numpy restatement of the GPU mask kernel
+accepted.  The token masks are additionally pinned against xgrammar (tests/
+test_fsm_vs_xgrammar.py): identical allowed-token sets on finite-language schemas, a subset
+on open ones (documented caps).  TokenFSM is the numpy restatement of the GPU mask kernel
 (csrc/sampler_fsm.cu: fsm_build_mask_kernel, sample_greedy_kernel's state advance).
 """
 from __future__ import annotations
