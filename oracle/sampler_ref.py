@@ -8,7 +8,8 @@ every token whose z is >= the k-th largest (ties kept); top-p then keeps the sma
 highest-z tokens whose softmax mass reaches top_p (ties kept); the token is drawn by inverse
 CDF over the kept set in vocabulary order from one uniform u per (seed, row, step).
 The generator is Philox4x32-10 (Salmon et al., SC'11), pinned by the Random123 known-answer
-vectors in tests/test_sampler_oracle.py.
+vectors in tests/test_sampler_oracle.py; the kept sets are checked there against
+transformers' Temperature / TopK / TopP logits warpers.
 """
 from __future__ import annotations
 

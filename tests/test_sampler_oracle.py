@@ -41,3 +41,36 @@ def test_inverse_cdf_in_vocabulary_order_and_uniform_range():
     assert 0.0 <= min(us) and max(us) < 1.0 and 0.35 < np.mean(us) < 0.65
     assert S.uniform(7, 3, 1, False) == S.uniform(7, 9, 1, False)      # shared stream
     assert S.uniform(7, 3, 1, True) != S.uniform(7, 9, 1, True)
+
+
+def test_kept_sets_match_transformers_logits_warpers():
+    """The filter semantics against transformers' Temperature / TopK / TopP warpers (applied
+    in that order, as `generate` does) on random logits: identical surviving-token sets.
+    Logits are drawn without ties and top_p is kept away from cumulative-mass boundaries, where
+    fp32 summation order decides membership."""
+    import torch
+    from transformers.generation.logits_process import (TemperatureLogitsWarper,
+                                                        TopKLogitsWarper, TopPLogitsWarper)
+    rng = np.random.default_rng(7)
+    checked = 0
+    for trial in range(60):
+        vocab = int(rng.choice([50, 333, 2048]))
+        logits = (rng.standard_normal(vocab) * rng.uniform(0.5, 4.0)).astype(np.float32)
+        T = float(rng.choice([0.5, 0.9, 1.0, 1.7]))
+        k = int(rng.choice([0, 1, 5, 40]))
+        p = float(rng.choice([1.0, 0.95, 0.8, 0.3]))
+        allowed = np.ones(vocab, dtype=bool)
+        keep, _ = S.kept_set(logits, allowed, T, k, p)
+        x = torch.from_numpy(logits)[None]
+        x = TemperatureLogitsWarper(T)(None, x)
+        if k > 0:
+            x = TopKLogitsWarper(top_k=k)(None, x)
+        if p < 1.0:
+            probs = torch.softmax(x[0].double(), -1).sort(descending=True).values.cumsum(0)
+            if (probs - p).abs().min() < 1e-4:      # boundary case: skip
+                continue
+            x = TopPLogitsWarper(top_p=p)(None, x)
+        theirs = torch.isfinite(x[0]).numpy()
+        assert (keep == theirs).all(), (trial, T, k, p, keep.sum(), theirs.sum())
+        checked += 1
+    assert checked > 40
