@@ -13,7 +13,9 @@
  *   - "device pointer" arguments are raw CUDA device addresses (PyTorch tensors'
  *     data_ptr() on the Python side); `stream` is a cudaStream_t passed as void*;
  *   - strings travel Arrow-style: one byte blob + int64 offsets[n+1];
- *   - the caller owns inputs; the engine owns outputs until sb200_result_free().
+ *   - the caller owns inputs; kernel- and engine-level calls write into caller-allocated
+ *     device buffers; sb200_infer_text() returns host buffers the library owns until
+ *     sb200_result_free().
  */
 #ifndef SUTRO_B200_H_
 #define SUTRO_B200_H_
@@ -230,6 +232,37 @@ int sb200_engine_set_vocab(void* engine, const uint8_t* tok_bytes, const int32_t
 /* blocking; returns when every row has finished (non-zero: see sb200_last_error) */
 int sb200_engine_run(void* engine, const sb200_job* job, sb200_job_stats* stats);
 void* sb200_engine_stream(void* engine);
+/* what a host needs to size buffers: the engine's CUDA device ordinal, whether it is an
+ * embedding model (prefill only), d_model and the vocabulary size (any pointer may be NULL) */
+int sb200_engine_info(void* engine, int* device, int* embedding_model, int* d_model, int* vocab);
+
+/* ------------------------------------------------------------------------
+ * The whole path in one call, HOST buffers in and out — what a non-Python host binds in
+ * place of `POST batch-inference` + `POST job-results` (sutro/sdk.py:223, :384-406).
+ * rows_bytes / rows_offsets[n_rows+1] are payload["inputs"] Arrow-style (sutro/sdk.py:197);
+ * `options` is an sb200_job whose prompt framing (prefix/suffix tokens), schema automaton,
+ * max_new_tokens, truncate_rows and sampling fields are used as given — its row-token,
+ * output and progress-independent device fields are ignored and filled in here.  The call
+ * copies the rows to HBM, tokenises, runs the engine, compacts and detokenises the outputs
+ * and copies them back; `*out` is owned by the library until sb200_result_free().
+ * results["outputs"][i] (sutro/sdk.py:406) = bytes[offsets[i] .. offsets[i+1]).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int64_t n_rows;
+  uint8_t* bytes;          /* UTF-8 of all outputs, concatenated (NULL when want_text = 0)   */
+  int64_t* offsets;        /* [n_rows+1] into bytes                                          */
+  int32_t* tokens;         /* generated token ids, concatenated                               */
+  int64_t* token_offsets;  /* [n_rows+1] into tokens                                          */
+  float* cum_logprob;      /* [n_rows] (results["cumulative_logprobs"]) or NULL               */
+  float* embeddings;       /* [n_rows, d_model] for embedding models, else NULL               */
+  int d_model;
+} sb200_result;
+
+int sb200_infer_text(void* engine, void* tokenizer, const uint8_t* rows_bytes,
+                     const int64_t* rows_offsets, int64_t n_rows, const sb200_job* options,
+                     int want_text, int want_logprobs, sb200_result** out,
+                     sb200_job_stats* stats);
+void sb200_result_free(sb200_result* result);
 
 #ifdef __cplusplus
 }

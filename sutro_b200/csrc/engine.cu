@@ -885,4 +885,17 @@ int sb200_engine_run(void* engine, const sb200_job* job, sb200_job_stats* stats)
 
 void* sb200_engine_stream(void* engine) { return static_cast<Engine*>(engine)->stream; }
 
+int sb200_engine_info(void* engine, int* device, int* embedding_model, int* d_model, int* vocab) {
+  if (!engine) {
+    set_last_error("engine_info: null engine");
+    return -1;
+  }
+  const auto* e = static_cast<const Engine*>(engine);
+  if (device) *device = e->device;
+  if (embedding_model) *embedding_model = e->cfg.embedding_model;
+  if (d_model) *d_model = e->cfg.d_model;
+  if (vocab) *vocab = e->cfg.vocab;
+  return 0;
+}
+
 }  // extern "C"

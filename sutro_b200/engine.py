@@ -93,6 +93,19 @@ L.register("sb200_tokenizer_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64
                                                C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p])
 
 
+class ResultC(C.Structure):          # sb200_result (include/sutro_b200.h)
+    _fields_ = [("n_rows", C.c_int64), ("bytes", c_u8p), ("offsets", c_i64p),
+                ("tokens", c_i32p), ("token_offsets", c_i64p), ("cum_logprob", C.POINTER(C.c_float)),
+                ("embeddings", C.POINTER(C.c_float)), ("d_model", C.c_int)]
+
+
+L.register("sb200_engine_info", C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4)
+L.register("sb200_infer_text", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.POINTER(JobC), C.c_int, C.c_int,
+                                         C.POINTER(C.POINTER(ResultC)), C.POINTER(JobStatsC)])
+L.register("sb200_result_free", None, [C.POINTER(ResultC)])
+
+
 def _np_ptr(a: np.ndarray, typ):
     return a.ctypes.data_as(typ)
 
@@ -507,6 +520,79 @@ class LocalEngine:
         return GenerationResult(outputs, out_tokens, emb, stats,
                                 None if d_first is None else d_first.cpu(),
                                 None if d_lp is None else d_lp.cpu().numpy())
+
+
+def _infer_one_call(self, rows, system_prompt: Optional[str] = None,
+                    json_schema: Optional[Dict[str, Any]] = None, max_new_tokens: int = 64,
+                    ignore_eos: bool = False, truncate_rows: bool = True,
+                    share_prefix: bool = True, fsm_limits: Optional[FsmLimits] = None,
+                    jump_forward: bool = True, temperature: float = 0.0, top_k: int = 0,
+                    top_p: float = 1.0, seed: int = 0, seed_per_row: bool = False,
+                    return_logprobs: bool = False) -> GenerationResult:
+    """The same job through `sb200_infer_text`: ONE C-ABI call with host buffers in and out
+    (what a non-Python host would bind).  `generate` is the phased form of the same work —
+    it keeps the phases apart so that the benchmark can time them; the results are identical."""
+    data, off = rows_to_blob(rows)
+    n_rows = len(off) - 1
+    emb_mode = self.spec.embedding_model
+    pre, suf = self._template_tokens(system_prompt)
+    dfa = self.compile_schema(json_schema, fsm_limits) if json_schema is not None else None
+    plan = None
+    if dfa is not None and jump_forward and not emb_mode:
+        plan = self._jump_plan(dfa, (id(dfa),))
+        if plan is not None and len(plan["prefix_tokens"]) >= max_new_tokens:
+            plan = None
+    if plan is not None:
+        suf = np.concatenate([suf, plan["prefix_tokens"]]).astype(np.int32)
+    data, off = np.ascontiguousarray(data), np.ascontiguousarray(off, dtype=np.int64)
+    job = JobC()
+    job.prefix_tokens, job.n_prefix = _np_ptr(pre, c_i32p), len(pre)
+    job.suffix_tokens, job.n_suffix = _np_ptr(suf, c_i32p), len(suf)
+    job.share_prefix, job.max_new_tokens = int(share_prefix), max_new_tokens
+    job.ignore_eos, job.truncate_rows = int(ignore_eos), int(truncate_rows)
+    if dfa is not None:
+        job.fsm_trans = _np_ptr(dfa.trans, c_i32p)
+        job.fsm_accept = _np_ptr(dfa.accept, c_u8p)
+        job.fsm_final = _np_ptr(dfa.final, c_u8p)
+        job.fsm_states, job.fsm_start = dfa.n_states, dfa.start
+        if plan is not None:
+            job.fsm_start = plan["start"]
+            job.n_forced_prefix = len(plan["prefix_tokens"])
+            job.fsm_tail_off = _np_ptr(plan["tail_off"], c_i32p)
+            job.fsm_tail_tok = _np_ptr(plan["tail_tok"], c_i32p)
+    job.temperature, job.top_k, job.top_p = float(temperature), int(top_k), float(top_p)
+    job.seed, job.seed_per_row = int(seed) & (2 ** 64 - 1), int(seed_per_row)
+    st, res = JobStatsC(), C.POINTER(ResultC)()
+    t0 = time.perf_counter()
+    L.check(L.lib().sb200_infer_text(self._h, self.tokenizer._h, data.ctypes.data, off.ctypes.data,
+                                     n_rows, C.byref(job), 1, int(return_logprobs),
+                                     C.byref(res), C.byref(st)))
+    try:
+        r = res.contents
+        outputs = out_tokens = emb = lp = None
+        if emb_mode:
+            emb = np.ctypeslib.as_array(r.embeddings, shape=(n_rows, r.d_model)).copy() \
+                if n_rows else np.zeros((0, self.spec.d_model), np.float32)
+        else:
+            toff = np.ctypeslib.as_array(r.token_offsets, shape=(n_rows + 1,)).copy()
+            toks = (np.ctypeslib.as_array(r.tokens, shape=(int(toff[-1]),)).copy()
+                    if toff[-1] else np.zeros(0, np.int32))
+            out_tokens = [toks[toff[i]:toff[i + 1]].tolist() for i in range(n_rows)]
+            boff = np.ctypeslib.as_array(r.offsets, shape=(n_rows + 1,)).copy()
+            blob = (np.ctypeslib.as_array(r.bytes, shape=(int(boff[-1]),)).copy()
+                    if boff[-1] else np.zeros(0, np.uint8))
+            outputs = blob_to_rows(blob, boff)
+            if return_logprobs and n_rows:
+                lp = np.ctypeslib.as_array(r.cum_logprob, shape=(n_rows,)).copy()
+    finally:
+        L.lib().sb200_result_free(res)
+    stats = {k: int(getattr(st, k)) for k in _STAT_INTS}
+    stats.update(n_rows=n_rows, t_total_s=time.perf_counter() - t0,
+                 output_tokens=0 if out_tokens is None else sum(map(len, out_tokens)))
+    return GenerationResult(outputs, out_tokens, emb, stats, None, lp)
+
+
+LocalEngine.infer_one_call = _infer_one_call
 
 
 # --------------------------------------------------------------------------- several GPUs, one process

@@ -53,3 +53,34 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """The Python mirrors of the C structs (engine.py) against the header itself: a probe
+    compiled with gcc prints sizeof/offsetof for every field."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from sutro_b200 import engine as E
+    mirrors = {"sb200_engine_config": E.EngineConfigC, "sb200_engine_weights": E.EngineWeightsC,
+               "sb200_job": E.JobC, "sb200_job_stats": E.JobStatsC, "sb200_result": E.ResultC}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
+    for cname, mirror in mirrors.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, *_ in mirror._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines.append("return 0;}")
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, what, value = line.split()
+        mirror = mirrors[cname]
+        want = ctypes.sizeof(mirror) if what == "size" else getattr(mirror, what).offset
+        assert int(value) == want, (cname, what, value, want)
+        seen += 1
+    assert seen == sum(len(m._fields_) + 1 for m in mirrors.values())

@@ -297,6 +297,32 @@ def test_row_ids_key_the_per_row_random_streams():
         eng.generate(rows[5:], row_ids=[1, 2], **kw)
 
 
+def test_one_call_c_entry_point_matches_the_phased_path():
+    """sb200_infer_text (host buffers in/out, one C call) vs LocalEngine.generate."""
+    spec, w, v, eng = build("tiny-qwen3", max_slots=8, max_prefill_tokens=512)
+    rows = synth.product_reviews(19, seed=6) + ["", None]
+    for kw in (dict(system_prompt=SYS, json_schema=SentimentEnum.model_json_schema(),
+                    max_new_tokens=32),
+               dict(system_prompt=SYS, max_new_tokens=9, ignore_eos=True),
+               dict(max_new_tokens=12, temperature=0.8, top_k=30, seed=4, seed_per_row=True)):
+        a = eng.generate(rows, return_tokens=True, return_logprobs=True, **kw)
+        b = eng.infer_one_call(rows, return_logprobs=True, **kw)
+        assert b.out_tokens == a.out_tokens and b.outputs == a.outputs
+        assert np.allclose(b.cum_logprobs, a.cum_logprobs, atol=1e-4)
+        assert b.stats["rows_done"] == len(rows)
+    assert eng.infer_one_call([], max_new_tokens=4).outputs == []
+    with pytest.raises(Exception):
+        eng.infer_one_call(rows, max_new_tokens=0)
+
+
+def test_one_call_c_entry_point_embedding_model():
+    spec, w, v, eng = build("tiny-qwen3-embedding", max_slots=8, max_prefill_tokens=256)
+    rows = synth.product_reviews(9, seed=2)
+    a = eng.generate(rows)
+    b = eng.infer_one_call(rows)
+    assert np.array_equal(a.embeddings, b.embeddings)
+
+
 def test_empty_and_null_inputs():
     spec, w, v, eng = build("tiny-qwen3", max_slots=4, max_prefill_tokens=256)
     assert eng.generate([], max_new_tokens=4).outputs == []
