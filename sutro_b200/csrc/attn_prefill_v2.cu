@@ -1,4 +1,13 @@
-// sutro_b200 — K3: causal prefill attention over the paged KV cache (varlen).
+// sutro_b200 — K3 (variant 2, opt-in with SB200_PREFILL_V2=1): causal prefill attention over
+// the paged KV cache.  Same work decomposition, tiles and math as attn_prefill.cu; what
+// changes is how the CTA's warps are coupled (ncu on variant 1: barrier stalls 1.8 and
+// long-scoreboard stalls 2.0 per issued instruction):
+//   * no __syncthreads in the main loop: every warp counts itself out of a super-tile with a
+//     shared-memory atomic, and the LAST warp to leave refills that ring stage — warps with
+//     different causal horizons no longer wait for each other;
+//   * Q goes global -> shared with 16-byte cp.async (coalesced) into a swizzled per-warp tile
+//     and is read back with ldmatrix, instead of 32 scattered 4-byte loads per thread.
+// Not yet measured on hardware; the default path is variant 1.
 //
 // The prompt's K/V have already been written to the cache by rope_kv_write, so
 // new tokens attend to [cached prefix | themselves] through one code path; a
@@ -11,8 +20,6 @@
 // copies of pre-swizzled tiles per stage, see kernels.h) so that one barrier
 // round and one softmax rescale cover 32 KV tokens; math is FlashAttention-2
 // style on mma.sync m16n8k16 with fp32 online softmax.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 
@@ -23,12 +30,13 @@ namespace {
 constexpr int kPfWarps = 8;
 constexpr int kPfStages = 3;                    // ring of 32-token super-tiles (2 pages)
 constexpr int kPfStageBytes = 4 * kTileBytes;   // K0 | V0 | K1 | V1
-constexpr int kPfSmem = kPfStages * kPfStageBytes + 1024;
+constexpr int kPfQBytes = kPfWarps * 16 * kHeadDim * 2;   // 16 q rows x 128 dims per warp
+constexpr int kPfSmem = kPfStages * kPfStageBytes + kPfQBytes + 1024;
 constexpr int kPfMaxPages = 1024;               // 16 k tokens of context per sequence
 
 template <int G>
 __global__ void __launch_bounds__(kPfWarps * 32, 2)
-attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+attn_prefill_v2_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
                     const __nv_bfloat16* __restrict__ kv_layer,
                     const int32_t* __restrict__ page_table, int max_pages,
                     const int32_t* __restrict__ work, const int32_t* __restrict__ seq_slot,
@@ -42,6 +50,8 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   // page ids of this sequence, staged once: the producer lane must not sit on a dependent
   // global load (page table -> bulk copy) in every iteration while 7 warps wait at the barrier
   __shared__ int32_t s_pt[kPfMaxPages];
+  // warps that have finished with super-tile i (the last one refills its ring stage)
+  __shared__ int32_t s_left[kPfMaxPages / 2 + 1];
 
   const int seq = work[2 * blockIdx.x];
   const int qt0 = work[2 * blockIdx.x + 1];
@@ -70,6 +80,7 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
     fence_mbar_init();
   }
   for (int i = threadIdx.x; i < n_pages; i += kPfWarps * 32) s_pt[i] = pt[i];
+  for (int i = threadIdx.x; i < n_super; i += kPfWarps * 32) s_left[i] = 0;
   __syncthreads();
 
   // one super-tile = up to two pages, each one flat 8 KiB copy (K tile + V tile)
@@ -88,26 +99,37 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   };
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < kPfStages - 1; ++s)
+    for (int s = 0; s < kPfStages; ++s)
       if (s < n_super) issue(s, s);
   }
 
-  // Q fragments for this warp's 16 tokens x 128 dims.
+  // Q: this warp's 16 tokens x 128 dims, global -> swizzled shared tile (16-byte chunk c of
+  // row r at c ^ (r & 7)) -> A fragments.  Rows past the sequence end are zero-filled.
   const int ldq = (hq + 2 * hkv) * kHeadDim;
   const int r0 = lane >> 2;
+  const int lm = lane >> 3;
+  const int lr = lane & 7;
   uint32_t qa[8][4];
   {
-    const int t0 = q0 + r0, t1 = q0 + r0 + 8;
-    const __nv_bfloat16* p0 =
-        qkv + static_cast<size_t>(q_start + t0) * ldq + head * kHeadDim + 2 * (lane & 3);
-    const __nv_bfloat16* p1 = p0 + static_cast<size_t>(8) * ldq;
-    const bool v0 = t0 < q_len, v1 = t1 < q_len;
+    const uint32_t qs = smem_u32(smem + kPfStages * kPfStageBytes + warp * (16 * kHeadDim * 2));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = i * 32 + lane;
+      const int row = idx >> 4, chunk = idx & 15;
+      const bool ok = q0 + row < q_len;
+      const __nv_bfloat16* src = qkv + static_cast<size_t>(q_start + (ok ? q0 + row : 0)) * ldq +
+                                 head * kHeadDim + chunk * 8;
+      cp_async_16(qs + row * 256 + ((chunk ^ (row & 7)) << 4), src, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
-      qa[kk][0] = v0 ? *reinterpret_cast<const uint32_t*>(p0 + kk * 16) : 0u;
-      qa[kk][1] = v1 ? *reinterpret_cast<const uint32_t*>(p1 + kk * 16) : 0u;
-      qa[kk][2] = v0 ? *reinterpret_cast<const uint32_t*>(p0 + kk * 16 + 8) : 0u;
-      qa[kk][3] = v1 ? *reinterpret_cast<const uint32_t*>(p1 + kk * 16 + 8) : 0u;
+      const int row = (lm & 1) * 8 + lr;
+      const int chunk = kk * 2 + (lm >> 1);
+      ldmatrix_x4(qs + row * 256 + ((chunk ^ (row & 7)) << 4), qa[kk][0], qa[kk][1], qa[kk][2],
+                  qa[kk][3]);
     }
   }
 
@@ -118,20 +140,9 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   float l_run[2] = {0.f, 0.f};
   const int pos_r0 = past + q0 + r0;  // absolute position of row r0 (row r0+8: +8)
 
-  const int lm = lane >> 3;
-  const int lr = lane & 7;
-
   for (int sup = 0; sup < n_super; ++sup) {
     const int stage = sup % kPfStages;
     const uint32_t phase = (sup / kPfStages) & 1;
-    // keep the ring full: the stage freed by the previous iteration's barrier
-    if (threadIdx.x == 0) {
-      const int nxt = sup + kPfStages - 1;
-      if (nxt < n_super) {
-        fence_proxy_async_smem();
-        issue(nxt, nxt % kPfStages);
-      }
-    }
     mbar_wait(smem_u32(&full_bar[stage]), phase);
 
     if (warp_active && sup * 32 <= warp_last_pos) {
@@ -220,7 +231,20 @@ attn_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         }
       }
     }
-    __syncthreads();  // everyone is done with this stage -> it may be refilled
+    // this warp is done with the stage; the last warp out refills it with super-tile sup + 3
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      const int before = atomicAdd(&s_left[sup], 1);
+      if (before == kPfWarps - 1) {
+        __threadfence_block();
+        const int nxt = sup + kPfStages;
+        if (nxt < n_super) {
+          fence_proxy_async_smem();
+          issue(nxt, stage);
+        }
+      }
+    }
   }
 
   if (warp_active) {
@@ -245,7 +269,7 @@ int launch(const void* qkv, void* out, const void* kv_layer, const int32_t* page
            int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
            const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past, int hq,
            int hkv, float scale, cudaStream_t stream) {
-  auto kern = attn_prefill_kernel<G>;
+  auto kern = attn_prefill_v2_kernel<G>;
   SB_SET_MAX_SMEM(kern, kPfSmem);
   dim3 grid(n_work, hkv);
   kern<<<grid, kPfWarps * 32, kPfSmem, stream>>>(
@@ -258,40 +282,20 @@ int launch(const void* qkv, void* out, const void* kv_layer, const int32_t* page
 
 }  // namespace
 
-int attn_prefill_q_tile(int hq, int hkv) { return 128 / (hq / hkv); }
-
-int attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
-                 int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
-                 const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past,
-                 int hq, int hkv, float scale, cudaStream_t stream) {
-  if (n_work <= 0) return 0;
-  if (hkv <= 0 || hq % hkv != 0) {
-    set_last_error("attn_prefill: hq=%d not a multiple of hkv=%d", hq, hkv);
-    return -1;
-  }
-  if (max_pages > kPfMaxPages) {
-    set_last_error("attn_prefill: max_pages=%d exceeds the staged page-table size %d", max_pages,
-                   kPfMaxPages);
-    return -1;
-  }
-  // opt-in variant (attn_prefill_v2.cu): decoupled warps, Q through shared memory
-  static const bool use_v2 = [] {
-    const char* e = std::getenv("SB200_PREFILL_V2");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (use_v2)
-    return attn_prefill_v2(qkv, out, kv_layer, page_table, max_pages, work, n_work, seq_slot,
-                           seq_q_start, seq_q_len, seq_past, hq, hkv, scale, stream);
+int attn_prefill_v2(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
+                    int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
+                    const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past,
+                    int hq, int hkv, float scale, cudaStream_t stream) {
 #define SB_PF(G)                                                                               \
   return launch<G>(qkv, out, kv_layer, page_table, max_pages, work, n_work, seq_slot,         \
                    seq_q_start, seq_q_len, seq_past, hq, hkv, scale, stream)
-  switch (hq / hkv) {
+  switch (hq / hkv) {   // arguments were validated by attn_prefill()
     case 1: SB_PF(1);
     case 2: SB_PF(2);
     case 4: SB_PF(4);
     case 8: SB_PF(8);
     default:
-      set_last_error("attn_prefill: unsupported GQA group size %d", hq / hkv);
+      set_last_error("attn_prefill_v2: unsupported GQA group size %d", hq / hkv);
       return -1;
   }
 #undef SB_PF
