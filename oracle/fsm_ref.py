@@ -12,7 +12,6 @@ on open ones (documented caps).  TokenFSM is the numpy restatement of the GPU ma
 """
 from __future__ import annotations
 
-import json
 from typing import Any, Dict, List
 
 import numpy as np
