@@ -59,6 +59,25 @@ def peaks():
             "source": "fallback"}
 
 
+def ncu_traffic(csv_name: str):
+    """DRAM bytes (read + write) of one launch from a committed `ncu --set full` capture under
+    profiles/ (first launch row of the raw-page CSV), or None.  The capture is of one
+    representative launch of the kernel class, not of this run."""
+    try:
+        import csv
+        with open(os.path.join(ROOT, "profiles", csv_name), newline="") as f:
+            rows = list(csv.reader(f))
+        hdr, units, first = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(key)
+            total += float(first[i]) * scale[units[i]]
+        return total
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled during the timed region."""
 
@@ -420,14 +439,21 @@ def main():
     attn_gbs = prof["attn_decode_bytes"] / (kms["attn_decode"] * 1e-3) / 1e9 if kms["attn_decode"] else 0.0
     roofline = {"kernel": "gemm_bf16_tn_kernel (tcgen05)", "bound": "tensor", "achieved": gemm_tf,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": gemm_tf / pk["bf16_tflops_sustained"], "traffic": None,
+                "frac": gemm_tf / pk["bf16_tflops_sustained"],
+                "traffic": ncu_traffic("r01_ncu_gemm_gateup_raw.csv"),
+                "traffic_note": "bytes of ONE gate-up GEMM launch (one prefill batch, M~15.4k, "
+                                "N=19456, K=2560; algorithmic ~478 MB) from the committed capture "
+                                "profiles/r01_ncu_gemm_gateup_raw.csv, not from this run",
                 "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                 "share_of_step": kms["gemm"] / tot_ms,
                 "launches": prof["kernel_launches"]["gemm"],
                 "avg_launch_ms": kms["gemm"] / max(1, prof["kernel_launches"]["gemm"])}
     roofline_attn = {"kernel": "attn_decode_kernel", "bound": "hbm", "achieved": attn_gbs,
                      "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": attn_gbs / pk["hbm_gbs"],
-                     "traffic": None, "share_of_step": kms["attn_decode"] / tot_ms,
+                     "traffic": ncu_traffic("r01_ncu_attn_decode_raw.csv"),
+                     "traffic_note": "bytes of ONE decode-attention launch in "
+                                     "profiles/r01_ncu_attn_decode_raw.csv",
+                     "share_of_step": kms["attn_decode"] / tot_ms,
                      "launches": prof["kernel_launches"]["attn_decode"]}
 
     cpu = None
