@@ -64,6 +64,15 @@ OPEN = {
     "number": obj(n={"type": "number"}),
     "nested_model": Order.model_json_schema(),
     "string_array": obj(tags={"type": "array", "items": {"type": "string"}}),
+    "wide_integer": obj(n={"type": "integer", "minimum": -3000, "maximum": 70000}),
+    "one_sided_integer": obj(n={"type": "integer", "minimum": 17}),
+    "decimal_range": obj(x={"type": "number", "minimum": 0.5, "maximum": 12.25}),
+    "pattern": obj(code={"type": "string", "pattern": "^[a-z]{2,4}-[0-9]+$"}),
+    "date": obj(day={"type": "string", "format": "date"}),
+    "uuid": obj(id={"type": "string", "format": "uuid"}),
+    "tuple": obj(t={"type": "array", "prefixItems": [{"type": "integer"}, {"type": "boolean"}],
+                    "items": False, "minItems": 2, "maxItems": 2}),
+    "mapping": obj(d={"type": "object", "additionalProperties": {"type": "boolean"}}),
 }
 
 
