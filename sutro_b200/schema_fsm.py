@@ -557,8 +557,11 @@ class _Compiler:
         "email": r"^[a-z0-9]{1,12}@[a-z0-9]{1,12}\.(com|org|net)$",
         "ipv4": r"^(25[0-5]|2[0-4]\d|1\d\d|[1-9]?\d)(\.(25[0-5]|2[0-4]\d|1\d\d|[1-9]?\d)){3}$",
         "uri": r"^https://[a-z0-9]{1,12}\.(com|org|net)(/[a-z0-9]{0,12})?$",
+        "duration": r"^PT(\d{1,2}H)?(\d{1,2}M)?\d{1,2}S$",
     }
-    _PLAIN_FORMATS = {"password", "binary", "byte", "regex"}   # annotations: nothing to enforce
+    # annotations: nothing to enforce
+    _PLAIN_FORMATS = {"password", "binary", "byte", "regex", "path", "file-path",
+                      "directory-path"}
 
     def string(self, sch) -> Frag:
         b = self.b
@@ -785,7 +788,19 @@ class _Compiler:
             if k in sch:
                 if set(sch) - self._ANNOTATIONS - {k}:
                     raise SchemaError(f"keywords next to {k} are not supported")
-                return b.alt(*[self.node(x) for x in sch[k]])
+                # an alternative this compiler cannot express is left out: the automaton
+                # then accepts a subset of the union, which keeps every output valid
+                alts, errors = [], []
+                for x in sch[k]:
+                    mark = (len(self.b.n.eps), len(self._ref_stack))
+                    try:
+                        alts.append(self.node(x))
+                    except SchemaError as e:
+                        errors.append(str(e))
+                        del self._ref_stack[mark[1]:]
+                if not alts:
+                    raise SchemaError(f"no alternative of {k} is supported: " + "; ".join(errors))
+                return alts[0] if len(alts) == 1 else b.alt(*alts)
         if "allOf" in sch:
             parts = list(sch["allOf"])
             rest = {k: v for k, v in sch.items() if k != "allOf"}

@@ -224,3 +224,24 @@ def test_pathological_patterns_are_refused_not_hung():
     dfa = compile_schema({"type": "string", "pattern": r"ab+c"}, FsmLimits())
     assert dfa.n_states < 10000 and dfa.matches(b'"' + b"x" * 30 + b"abbc" + b"y" * 30 + b'"')
     assert not dfa.matches(b'"' + b"x" * 40 + b"abbc" + b"y" * 30 + b'"')
+
+
+def test_unions_keep_the_alternatives_that_can_be_expressed():
+    """pydantic's Decimal is number | string-with-a-lookahead-pattern: the number form is kept,
+    so the field still works; a union with no expressible alternative raises."""
+    import ipaddress
+    import pathlib
+    from decimal import Decimal as D
+
+    class Money(BaseModel):
+        amount: D
+        wait: datetime.timedelta
+        host: ipaddress.IPv4Address
+        where: pathlib.Path
+
+    dfa = compile_schema(Money.model_json_schema(), LIM)
+    rng = np.random.RandomState(3)
+    for _ in range(150):
+        Money.model_validate_json(random_accepted(dfa, rng))
+    with pytest.raises(SchemaError):
+        compile_schema({"anyOf": [{"type": "string", "pattern": r"(?=a)b"}, {"not": {}}]}, LIM)
