@@ -1014,7 +1014,9 @@ def _intersect(a: "ByteDFA", c: "ByteDFA") -> "ByteDFA":
 
 
 # --------------------------------------------------------------------------- NFA -> DFA
-_MAX_DFA_STATES = 200_000     # 200 k states = 200 MB of transitions; beyond that, refuse
+# The mask-build kernel runs one grid row per state (grid.y <= 65535), and every state costs
+# vocab/8 bytes of mask in HBM (19 KB at a 152 k vocabulary); larger automata are refused.
+_MAX_DFA_STATES = 65_535
 
 
 def _determinise(nfa: _NFA, start: int, end: int) -> ByteDFA:
