@@ -14,7 +14,7 @@ min-/maxProperties), string (minLength/maxLength, pattern, format date / date-ti
 uuid / email / ipv4 / uri, enum, const), integer / number (minimum / maximum / exclusive
 bounds — exact digit automata — and multipleOf over small ranges), boolean, null, enum of
 JSON literals, array (items, prefixItems, minItems/maxItems, uniqueItems over small enums),
-anyOf/oneOf, allOf of compatible parts, $ref/$defs (non-recursive).  A keyword that would
+anyOf/oneOf, allOf of compatible parts, $ref/$defs (recursion unrolled to a fixed depth).  A keyword that would
 constrain the output but is not implemented raises SchemaError — nothing is silently
 ignored.  Unbounded strings / arrays / digits / repeats get explicit caps (`FsmLimits`) so
 that every path through the automaton terminates — with random weights a model never chooses
@@ -39,6 +39,7 @@ class FsmLimits:
     max_int_digits: int = 9        # digits of an unbounded integer
     max_frac_digits: int = 4
     small_int_range: int = 2048    # ranges up to this size are encoded exactly
+    max_recursion: int = 2         # how often a recursive $ref may be re-entered
 
 
 @dataclass
@@ -615,7 +616,12 @@ class _Compiler:
             if lo > 0:
                 raise SchemaError("array admits no items but minItems > 0")
             return b.lit(b"[]")
-        first = self.node(items)
+        try:
+            first = self.node(items)
+        except SchemaError:
+            if lo > 0:
+                raise
+            return b.lit(b"[]")      # items cannot be expressed (recursion floor): stay empty
         rest = b.rep(lambda: b.seq(b.lit(b","), self.node(items)), max(lo - 1, 0), hi - 1)
         inner = b.seq(first, rest)
         if lo == 0:
@@ -771,8 +777,12 @@ class _Compiler:
             ref = sch["$ref"]
             if set(sch) - self._ANNOTATIONS - {"$ref"}:
                 raise SchemaError("keywords next to $ref are not supported")
-            if ref in self._ref_stack:
-                raise SchemaError(f"recursive schema through {ref} is not supported")
+            if self._ref_stack.count(ref) > self.lim.max_recursion:
+                # a DFA has no stack: recursion is unrolled to a fixed depth; at the bottom the
+                # enclosing array becomes [] / the enclosing union drops this alternative
+                raise SchemaError(f"recursion through {ref} is deeper than "
+                                  f"{self.lim.max_recursion} levels and nothing encloses it "
+                                  "that could stop (an array with minItems 0, a union)")
             self._ref_stack.append(ref)
             try:
                 return self.node(self.resolve(ref))

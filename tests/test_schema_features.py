@@ -245,3 +245,32 @@ def test_unions_keep_the_alternatives_that_can_be_expressed():
         Money.model_validate_json(random_accepted(dfa, rng))
     with pytest.raises(SchemaError):
         compile_schema({"anyOf": [{"type": "string", "pattern": r"(?=a)b"}, {"not": {}}]}, LIM)
+
+
+def test_recursive_models_are_unrolled_to_a_fixed_depth():
+    class Node(BaseModel):
+        value: int = Field(ge=0, le=9)
+        children: List["Node"] = Field(default_factory=list, max_length=2)
+
+    class Linked(BaseModel):
+        tag: Literal["x", "y"]
+        next: Optional["Linked"] = None
+
+    for model in (Node, Linked):
+        schema = model.model_json_schema()
+        dfa = compile_schema(schema, LIM)
+        rng = np.random.RandomState(2)
+        depths = set()
+        for _ in range(200):
+            text = random_accepted(dfa, rng)
+            model.model_validate_json(text)
+            depths.add(text.count(b"[") + text.count(b"{") - 1)
+        assert max(depths) >= 2                      # nesting really is produced
+    leaf = {"value": 1, "children": []}
+    mid = {"value": 2, "children": [leaf, leaf]}
+    assert accepts(Node.model_json_schema(), {"value": 3, "children": [mid]})
+    too_deep = {"value": 0, "children": [{"value": 0, "children": [{"value": 0, "children": [leaf]}]}]}
+    assert not accepts(Node.model_json_schema(), too_deep)
+    with pytest.raises(SchemaError):                 # a cycle with no way to stop
+        compile_schema({"$defs": {"A": {"type": "object", "properties": {"a": {"$ref": "#/$defs/A"}},
+                                        "required": ["a"]}}, "$ref": "#/$defs/A"}, LIM)

@@ -89,9 +89,15 @@ def test_string_escapes_and_utf8():
 
 
 def test_unsupported_schema_raises_value_error():
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError):      # a cycle nothing can stop (a required self-reference)
         compile_schema({"type": "object", "properties": {"x": {"$ref": "#/$defs/T"}},
-                        "$defs": {"T": {"type": "array", "items": {"$ref": "#/$defs/T"}}}})
+                        "$defs": {"T": {"type": "object", "properties": {"t": {"$ref": "#/$defs/T"}},
+                                        "required": ["t"]}}})
+    # a cycle through an array is unrolled to a fixed depth and bottoms out in []
+    nested = compile_schema({"type": "object", "properties": {"x": {"$ref": "#/$defs/T"}},
+                             "$defs": {"T": {"type": "array", "items": {"$ref": "#/$defs/T"},
+                                             "maxItems": 2}}})
+    assert nested.matches(b'{"x":[[],[[]]]}') and not nested.matches(b'{"x":[[[[[]]]]]}')
     with pytest.raises(SchemaError):
         compile_schema({"type": "frobnicate"})
 
