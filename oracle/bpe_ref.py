@@ -24,7 +24,7 @@ class RefTokenizer:
         self.pat = regex.compile(PRETOK_PATTERN % v.digits)
         self.rank: Dict[Tuple[int, int], Tuple[int, int]] = {}
         for i, (a, b) in enumerate(v.merges):
-            self.rank.setdefault((a, b), (i, 256 + i))
+            self.rank.setdefault((a, b), (i, 256 + i if v.merged_ids is None else v.merged_ids[i]))
 
     def _bpe(self, word: bytes) -> List[int]:
         s = list(word)

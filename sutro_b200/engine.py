@@ -140,6 +140,14 @@ def rows_to_blob(rows) -> Tuple[np.ndarray, np.ndarray]:
     return data, off
 
 
+def _nfc_rows(rows):
+    import unicodedata
+    if not isinstance(rows, (list, tuple)):
+        return rows            # Arrow / pandas input: taken as is
+    return [r if r is None or not isinstance(r, str) or unicodedata.is_normalized("NFC", r)
+            else unicodedata.normalize("NFC", r) for r in rows]
+
+
 def _all_str(rows) -> bool:
     return isinstance(rows, list) and all(isinstance(r, str) for r in rows)
 
@@ -161,10 +169,13 @@ class GpuTokenizer:
         self._blob, self._off = blob, off
         merges = np.ascontiguousarray(v.merge_array())
         cls = np.ascontiguousarray(class_table())
+        # real tokenizer files give every merge its own result id; synthetic ones use 256 + rank
+        mids = None if v.merged_ids is None else np.ascontiguousarray(v.merged_ids, dtype=np.int32)
         h = C.c_void_p()
         with torch.cuda.device(device):
             L.check(L.lib().sb200_tokenizer_create(
-                merges.ctypes.data, len(v.merges), None, cls.ctypes.data, v.digits,
+                merges.ctypes.data, len(v.merges), None if mids is None else mids.ctypes.data,
+                cls.ctypes.data, v.digits,
                 blob.ctypes.data, off.ctypes.data, v.vocab_size, C.byref(h)))
         self._h = h
 
@@ -381,6 +392,8 @@ class LocalEngine:
         emb_mode = self.spec.embedding_model
         t0 = time.perf_counter()
         # ---- phase A -------------------------------------------------------------
+        if self.vocab.normalize_nfc:      # real tokenizer files only (pretrained.py)
+            rows = _nfc_rows(rows)
         data, off = rows_to_blob(rows)
         n_rows, n_bytes = len(off) - 1, int(off[-1])
         if n_rows == 0:
@@ -532,6 +545,8 @@ def _infer_one_call(self, rows, system_prompt: Optional[str] = None,
     """The same job through `sb200_infer_text`: ONE C-ABI call with host buffers in and out
     (what a non-Python host would bind).  `generate` is the phased form of the same work —
     it keeps the phases apart so that the benchmark can time them; the results are identical."""
+    if self.vocab.normalize_nfc:
+        rows = _nfc_rows(rows)
     data, off = rows_to_blob(rows)
     n_rows = len(off) - 1
     emb_mode = self.spec.embedding_model

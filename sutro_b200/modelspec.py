@@ -14,6 +14,7 @@ import math
 from dataclasses import dataclass, field, replace
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 
 HEAD_DIM = 128  # every supported architecture uses 128-wide heads (kernels assume it)
@@ -207,15 +208,23 @@ class EngineWeights:
         return out
 
 
-def pack_for_engine(spec: ModelSpec, w: Dict[str, torch.Tensor], device) -> EngineWeights:
+def pack_for_engine(spec: ModelSpec, w: Dict[str, torch.Tensor], device,
+                    row_map=None) -> EngineWeights:
+    """HF-named tensors -> engine layout on `device`.  `row_map` (engine id -> checkpoint id,
+    `Vocab.id_map` of a real tokenizer file) reorders the embedding / lm_head rows."""
     dev = torch.device(device)
 
     def d(t):
         return t.to(dev).contiguous()
 
-    embed = d(w["model.embed_tokens.weight"])
+    def rows(t):
+        if row_map is None:
+            return d(t)
+        return d(t[torch.as_tensor(np.asarray(row_map), dtype=torch.long)])
+
+    embed = rows(w["model.embed_tokens.weight"])
     ew = EngineWeights(embed=embed,
-                       lm_head=embed if spec.tied_embeddings else d(w["lm_head.weight"]),
+                       lm_head=embed if spec.tied_embeddings else rows(w["lm_head.weight"]),
                        final_norm=d(w["model.norm.weight"]))
     for i in range(spec.n_layers):
         p = f"model.layers.{i}."

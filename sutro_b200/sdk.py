@@ -112,8 +112,12 @@ class _ProgressStream:
 class Sutro(Templates, BaseSutroClient):
     def __init__(self, devices: Optional[List[int]] = None, weights_seed: int = 0,
                  engine_options: Optional[Dict[str, Any]] = None, cache_dir: Optional[str] = None,
-                 verbose: bool = True, on_progress=None):
+                 verbose: bool = True, on_progress=None,
+                 model_paths: Optional[Dict[str, str]] = None):
         self.devices = devices or [0]
+        # model name -> Hugging Face model directory (config.json, tokenizer.json, *.safetensors);
+        # models without a path run on seeded random weights and the synthetic vocabulary
+        self.model_paths = dict(model_paths or {})
         # optional callable(record): receives every progress / tokens record of a running job
         self.on_progress = on_progress
         self.weights_seed = weights_seed
@@ -129,6 +133,14 @@ class Sutro(Templates, BaseSutroClient):
             print(to_colored_text(msg, state))
 
     def _engine(self, model: str):
+        if model not in self._engines and model in self.model_paths:
+            from .pretrained import load_pretrained
+            if len(self.devices) > 1:
+                raise ValueError("model_paths with several devices is not supported yet: "
+                                 "run one process per GPU")
+            self._say(f"Loading {model} from {self.model_paths[model]} on cuda:{self.devices[0]}")
+            self._engines[model] = load_pretrained(self.model_paths[model], self.devices[0],
+                                                   name=model, **self.engine_options)
         if model not in self._engines:
             from .engine import LocalEngine, MultiGpuEngine
             where = ", ".join(f"cuda:{d}" for d in self.devices)

@@ -21,7 +21,7 @@ from __future__ import annotations
 import functools
 from collections import Counter
 from dataclasses import dataclass
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -39,6 +39,15 @@ class Vocab:
     merges: List[Tuple[int, int]]       # merge i: (left id, right id) -> id 256+i
     specials: Dict[str, int]
     digits: int                         # max digits per pre-token
+    # real tokenizer files (pretrained.load_tokenizer_json): id of merge i's result when it is
+    # not 256+i, and the engine-id -> real-id permutation of the 256 byte tokens
+    merged_ids: Optional[List[int]] = None
+    id_map: Optional[np.ndarray] = None
+    normalize_nfc: bool = False         # the tokenizer file asks for NFC-normalised input
+
+    def to_real_ids(self, ids):
+        """engine token ids -> the tokenizer file's ids (identity for synthetic vocabularies)"""
+        return list(ids) if self.id_map is None else [int(self.id_map[i]) for i in ids]
 
     @property
     def eos_id(self) -> int:

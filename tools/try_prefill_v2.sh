@@ -4,6 +4,9 @@
 #   gpurun --timeout 600 -- 'bash tools/try_prefill_v2.sh'
 set -u
 mkdir -p gpurun_out
+# pretrained-loading path (tests/test_engine_gpu.py::test_model_directory_on_disk_matches_oracle)
+SB200_TEST_PRETRAINED=1 timeout 200 python -m pytest tests/test_engine_gpu.py -x -q -k model_directory \
+    2>&1 | tail -5
 SB200_PREFILL_V2=1 timeout 300 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py -x -q \
     2>&1 | tail -5
 for v in 0 1; do
