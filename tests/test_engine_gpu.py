@@ -389,8 +389,6 @@ def test_model_directory_on_disk_matches_oracle(name, tmp_path):
     compared = total = 0
     for row, got in zip(ROWS, res.out_tokens):
         prompt = loaded.to_real_ids(ref_tok.render(tpl, row, spec.max_position - 12))
-        assert prompt == hf.encode("".join(p for p in tpl.prefix) + row + "".join(tpl.suffix)).ids \
-            or True      # (special-token pieces are tokenised separately; informational only)
         r = model.generate(prompt, 12, real_eos, ignore_eos=True)
         c, t, _ = compare_greedy(loaded.to_real_ids(got), r, row[:30], real_eos)
         compared, total = compared + c, total + t
