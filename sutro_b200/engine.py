@@ -333,7 +333,8 @@ class LocalEngine:
         key = (system_prompt, self.spec.embedding_model)
         if key not in self._tpl_cache:
             tpl = (VB.embedding_template(self.spec.family) if self.spec.embedding_model
-                   else VB.chat_template(self.spec.family, system_prompt))
+                   else VB.chat_template(self.spec.family, system_prompt,
+                                         getattr(self, "empty_think_block", False)))
             pre = np.asarray(self.tokenizer.encode_pieces(tpl.prefix), dtype=np.int32)
             suf = np.asarray(self.tokenizer.encode_pieces(tpl.suffix), dtype=np.int32)
             self._tpl_cache[key] = (pre, suf)

@@ -197,4 +197,8 @@ def load_pretrained(model_dir: str, device=0, name: Optional[str] = None,
     w = load_hf_weights(model_dir)
     ew = MS.pack_for_engine(spec, w, device if isinstance(device, str) else f"cuda:{device}",
                             row_map=v.id_map)
-    return LocalEngine(spec, ew, v, device=device, **engine_kw)
+    eng = LocalEngine(spec, ew, v, device=device, **engine_kw)
+    # released Qwen3 chat models answer directly only when the turn opens with an empty think block
+    eng.empty_think_block = (spec.family == "qwen3" and not spec.embedding_model
+                             and "thinking" not in name.lower())
+    return eng

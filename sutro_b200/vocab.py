@@ -174,13 +174,19 @@ class Template:
     suffix: List[str]
 
 
-def chat_template(family: str, system_prompt: str | None) -> Template:
+def chat_template(family: str, system_prompt: str | None,
+                  empty_think_block: bool = False) -> Template:
+    """`empty_think_block`: Qwen3's released template in non-thinking mode opens the answer with
+    an empty `<think>` block; real Qwen3 checkpoints are served that way (pretrained.py), the
+    synthetic benchmark models are not (there is nothing to suppress)."""
     if family == "qwen3":
         pre: List[str] = []
         if system_prompt:
             pre += ["<|im_start|>", "system\n" + system_prompt, "<|im_end|>", "\n"]
         pre += ["<|im_start|>", "user\n"]
         suf = ["<|im_end|>", "\n", "<|im_start|>", "assistant\n"]
+        if empty_think_block:
+            suf[-1] += "<think>\n\n</think>\n\n"
         return Template(pre, suf)
     pre = ["<|begin_of_text|>"]
     if system_prompt:
