@@ -186,7 +186,9 @@ def chat_template(family: str, system_prompt: str | None,
         pre += ["<|im_start|>", "user\n"]
         suf = ["<|im_end|>", "\n", "<|im_start|>", "assistant\n"]
         if empty_think_block:
-            suf[-1] += "<think>\n\n</think>\n\n"
+            # <think> / </think> are added tokens of the Qwen3 vocabulary: separate pieces, so
+            # that they map to their own ids when the tokenizer file defines them
+            suf += ["<think>", "\n\n", "</think>", "\n\n"]
         return Template(pre, suf)
     pre = ["<|begin_of_text|>"]
     if system_prompt:
