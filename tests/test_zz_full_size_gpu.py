@@ -1,5 +1,5 @@
 """BASELINE.json configs[1] at FULL size (20,000 rows, qwen-3-4b architecture, bf16) through
-size-independent properties — the CPU oracle cannot run this size, so the checks are the ones
+size-independent properties (the file name sorts it last: it is the heaviest test) — the CPU oracle cannot run this size, so the checks are the ones
 the domain offers:
 
 * every output parses as JSON and validates against the schema (constrained decoding is exact);
