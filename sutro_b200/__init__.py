@@ -19,7 +19,9 @@ from .sdk import Sutro  # noqa: F401
 _instance = None
 _PUBLIC = ["infer", "infer_per_model", "await_job_completion", "get_job_results",
            "get_job_status", "fetch_job", "list_jobs", "cancel_job", "get_job_embeddings",
-           "register_engine", "classify", "embed", "score"]
+           "register_engine", "classify", "embed", "score", "rank", "elo", "attach",
+           "set_api_key", "set_base_url", "set_serving_base_url", "get_quotas",
+           "try_authentication"]
 
 
 def _client() -> Sutro:

@@ -433,6 +433,33 @@ class Sutro(Templates, BaseSutroClient):
         list-of-lists results column)."""
         return self._job(job_id).embeddings
 
-    # quotas / datasets / auth are properties of the hosted service, not of this path
+    # quotas / datasets / auth are properties of the hosted service, not of this path; the
+    # calls scripts written for the reference make at start-up are accepted and do nothing
     def try_authentication(self, api_key: str = None):
         return {"authenticated": True, "backend": "local-b200"}
+
+    def set_api_key(self, api_key: str):                 # sutro/sdk.py:58-71
+        self.api_key = api_key
+
+    def set_base_url(self, base_url: str):               # sutro/sdk.py:73-83
+        self.base_url = base_url
+
+    def set_serving_base_url(self, serving_base_url: str):
+        self.serving_base_url = serving_base_url
+
+    def get_quotas(self):                                # sutro/sdk.py:1477-1491
+        return [{"job_priority": p, "row_quota": None, "token_quota": None} for p in (0, 1)]
+
+    def attach(self, job_id):                            # sutro/sdk.py:759-870
+        """Jobs run synchronously here, so attaching reports the final state."""
+        j = self._job(job_id)
+        self._say(f"Job {job_id}: {j.status.value} ({j.n_rows} rows)",
+                  "success" if j.status == JobStatus.SUCCEEDED else None)
+        return j.status
+
+    def _no_datasets(self, *a, **kw):
+        raise NotImplementedError("datasets are a feature of the hosted service; pass lists, "
+                                  "DataFrames or csv / parquet / txt paths to infer()")
+
+    create_dataset = upload_to_dataset = list_datasets = list_dataset_files = \
+        download_from_dataset = _no_datasets

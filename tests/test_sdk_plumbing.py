@@ -395,3 +395,22 @@ def test_multi_gpu_engine_merges_shard_progress_and_scatters_rows():
     assert a.got[1] == [0, 1, 2] and b.got[1] == [3, 4, 5] and blocks.outputs[3] == "xxxxxxx@b"
     with pytest.raises(ValueError):
         MultiGpuEngine([a, b]).generate(rows, balance="tokens")
+
+
+def test_start_up_calls_of_reference_scripts_are_accepted():
+    """`so.set_api_key(...)`, `so.set_base_url(...)`, `so.get_quotas()`, `so.attach(id)` exist
+    (sutro/sdk.py:58-95, :759, :1477); dataset calls say where datasets live."""
+    c = client()
+    c.set_api_key("sk-test")
+    c.set_base_url("https://example.invalid")
+    c.set_serving_base_url("https://example.invalid")
+    assert c.try_authentication("sk-test")["authenticated"] is True
+    assert {q["job_priority"] for q in c.get_quotas()} == {0, 1}
+    jid = c.infer(["a"], model="qwen-3-4b", stay_attached=False)
+    assert c.attach(jid) == interfaces.JobStatus.SUCCEEDED
+    with pytest.raises(NotImplementedError):
+        c.create_dataset()
+    with pytest.raises(NotImplementedError):
+        c.upload_to_dataset("d", ["f.parquet"])
+    for name in ("set_api_key", "set_base_url", "get_quotas", "attach", "rank", "elo", "infer"):
+        assert callable(getattr(so, name))
