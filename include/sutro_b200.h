@@ -89,6 +89,17 @@ int sb200_attn_prefill(const void* qkv, void* out, const void* kv_layer, const i
                        const int32_t* seq_past, int hq, int hkv, float scale, void* stream);
 int sb200_attn_prefill_q_tile(int hq, int hkv);
 
+/* K3 on tcgen05 tensor cores (the engine's prefill path): causal varlen attention over DENSE
+ * K/V.  qkv:[t_rows, (hq+2*hkv)*128] holds q AND the post-norm/RoPE k, v of the new tokens
+ * (what sb200_gemm_qkv_rope leaves there); prefix_kv:[n_layers, prefix_rows, 2*hkv*128]
+ * (K heads | V heads) holds the shared prefix, NULL when no sequence has a past.
+ * items:[n_items] {seq, q_tile_start}; sequence i attends to prefix rows [0, seq_past[i])
+ * and to its own rows [seq_q_start[i], +seq_q_len[i]) causally. */
+int sb200_attn_prefill_dense(const void* qkv, int t_rows, void* out, const void* prefix_kv,
+                             int prefix_rows, int n_layers, int layer, const int32_t* items,
+                             int n_items, const int32_t* seq_q_start, const int32_t* seq_q_len,
+                             const int32_t* seq_past, int hq, int hkv, float scale, void* stream);
+
 /* K8: token-level mask of a byte DFA compiled from output_schema. */
 int sb200_fsm_build_mask(const int32_t* fsm_trans, const uint8_t* fsm_accept, int n_states,
                          const uint8_t* tok_bytes, const int32_t* tok_off, int vocab, int eos_id,
@@ -223,6 +234,10 @@ typedef struct {
   double kernel_ms[SB200_KC_COUNT];        /* device time per class (job.profile only)    */
   double gemm_flops;                       /* 2*M*N*K summed over every GEMM launch       */
   double attn_decode_bytes;                /* K/V bytes the decode attention had to read  */
+  /* sb200_infer_text only: CUDA-event times on the engine's stream.  h2d = the rows' bytes and
+   * offsets host -> HBM; device = tokenise -> prefill/decode -> detokenise with inputs and
+   * outputs resident in HBM; d2h = result buffers HBM -> host.                                */
+  double t_h2d_ms, t_device_ms, t_d2h_ms;
 } sb200_job_stats;
 
 int sb200_engine_create(const sb200_engine_config* cfg, const sb200_engine_weights* w, void** out);
@@ -263,6 +278,22 @@ int sb200_infer_text(void* engine, void* tokenizer, const uint8_t* rows_bytes,
                      int want_text, int want_logprobs, sb200_result** out,
                      sb200_job_stats* stats);
 void sb200_result_free(sb200_result* result);
+
+/* Device-side Arrow helpers used by the Python host instead of tensor-library ops.
+ * compact_rows: out_tokens[n_rows, stride] with len[i] valid tokens per row -> off[n_rows+1]
+ * and the flat token array (capacity n_rows*stride).
+ * rows_select: pick m rows of a device-resident string column by index (row sharding across
+ * GPUs; the ordered gather of per-rank results on rank 0: results["outputs"] stay positional,
+ * sutro/sdk.py:406-412).  The source may be a batch of equally strided columns — row j is row
+ * j % part_rows of part j / part_rows, whose offsets start at off[part*(part_rows+1)] and whose
+ * bytes start at bytes + part*part_bytes (what a gather of padded per-rank buffers looks like);
+ * a plain column is part_rows = its row count, part_bytes = 0.  out_bytes needs room for the
+ * selected rows (the source size always suffices). */
+int sb200_compact_rows(const int32_t* out_tokens_dev, const int32_t* out_len_dev, int64_t n_rows,
+                       int stride, int64_t* off_dev, int32_t* flat_dev, void* stream);
+int sb200_rows_select(const uint8_t* bytes_dev, const int64_t* off_dev, int64_t part_rows,
+                      int64_t part_bytes, const int64_t* idx_dev, int64_t m, int64_t* out_off_dev,
+                      uint8_t* out_bytes_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,8 @@ class GenResult:
     finished_by: str            # "eos" | "fsm" | "length"
     runner_up: Optional[List[int]] = None   # second-best allowed token at each decision
     decision_pos: Optional[List[int]] = None  # index into `tokens` of each decision (EOS: len)
+    near: Optional[List[Dict[int, float]]] = None  # per decision: {token: top1 - logit} of the
+                                                   # (up to 8) best allowed tokens
 
 
 class RefModel:
@@ -163,6 +165,7 @@ class RefModel:
         margins: List[float] = []
         second: List[int] = []
         dpos: List[int] = []
+        near: List[Dict[int, float]] = []
         state = fsm.start if fsm is not None else None
         pos = len(prompt)
         why = "length"
@@ -171,7 +174,9 @@ class RefModel:
             if fsm is not None:
                 allowed = fsm.allowed(state)
                 lg = torch.where(allowed, lg, torch.full_like(lg, float("-inf")))
-            top = torch.topk(lg, 2)
+            top = torch.topk(lg, min(8, lg.numel()))
+            near.append({int(i): float(top.values[0] - v) for v, i in zip(top.values, top.indices)
+                         if v > float("-inf")})
             # lowest index wins exact ties, like the engine's sampler
             best = top.values[0]
             tok = int((lg == best).nonzero()[0])
@@ -196,4 +201,4 @@ class RefModel:
                 break
             h = self._forward([tok], pos, cache)
             pos += 1
-        return GenResult(out, margins, why, second, dpos)
+        return GenResult(out, margins, why, second, dpos, near)

@@ -35,6 +35,9 @@ _SIGNATURES = {
     "sb200_attn_prefill": (c_int, [c_void_p] * 4 + [c_int, c_void_p, c_int] + [c_void_p] * 4 +
                            [c_int, c_int, c_float, c_void_p]),
     "sb200_attn_prefill_q_tile": (c_int, [c_int, c_int]),
+    "sb200_attn_prefill_dense": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                         c_int, c_float, c_void_p]),
     "sb200_fsm_build_mask": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                                      c_void_p, c_int, c_void_p]),
 }

@@ -367,8 +367,12 @@ int launch(const void* qkv, void* out, const void* kv_layer, const int32_t* page
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // enough pairs to give every resident warp (2 CTAs x 4 warps per SM) a few of its own
-  if ((n_pairs >= sms * 2 * kDecWarps * 2 && !g_force_split) || g_force_warp) {
+  // The warp-per-(sequence, kv head) kernel is the only one the engine uses: which kernel
+  // runs must not depend on the batch size, or a row's greedy tokens would depend on its
+  // neighbours (the two kernels merge partial softmaxes in different orders).  The 4-warp
+  // split kernel stays for explicit requests (tests, latency experiments).
+  (void)sms;
+  if (!g_force_split || g_force_warp) {
     auto wk = attn_decode_warp_kernel<G>;
     SB_SET_MAX_SMEM(wk, kDecSmem);
     wk<<<(n_pairs + kDecWarps - 1) / kDecWarps, kDecWarps * 32, kDecSmem, stream>>>(

@@ -13,6 +13,7 @@
 // chunk, the page table and the per-slot decode state.
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -219,6 +220,12 @@ struct Engine {
   double gemm_flops = 0, attn_decode_bytes = 0;
   int device = 0;
   bool fuse_qkv = true;  // SB200_FUSE_QKV=0 keeps the separate rope_kv_write kernel (A/B tests)
+  // tcgen05 prefill attention over dense K/V (attn_prefill_tc.cu); SB200_PREFILL_TC=0 falls
+  // back to the paged mma.sync kernel (A/B tests)
+  bool prefill_tc = true;
+  bf16* prefix_kv = nullptr;  // [n_layers][prefix_rows][2*hkv*128]: dense K|V of the shared prefix
+  int prefix_rows = 0;
+  bool fill_prefix = false;   // this forward pass is the prefix prefill: keep its K/V
 
   ~Engine() {
     for (void* p : {(void*)x, (void*)h, (void*)qkv, (void*)attn, (void*)act, (void*)hl, (void*)hn,
@@ -229,7 +236,7 @@ struct Engine {
                     (void*)slot_maxnew, (void*)slot_cum_logprob, (void*)d_stage, (void*)d_tok_bytes, (void*)d_tok_off,
                     (void*)d_fsm_trans, (void*)d_fsm_accept, (void*)d_fsm_final,
                     (void*)d_mask_bits, (void*)d_prefix, (void*)d_suffix, (void*)d_tail_off,
-                    (void*)d_tail_tok})
+                    (void*)d_tail_tok, (void*)prefix_kv})
       cudaFree(p);
     if (h_stage) cudaFreeHost(h_stage);
     if (h_done) cudaFreeHost(h_done);
@@ -249,6 +256,7 @@ struct Engine {
     num_pages = c.num_pages;
     layer_stride = static_cast<size_t>(num_pages) * c.n_kv_heads * 2 * kTileElems;
     if (const char* e = getenv("SB200_FUSE_QKV")) fuse_qkv = e[0] != '0';
+    if (const char* e = getenv("SB200_PREFILL_TC")) prefill_tc = e[0] != '0';
     SB_CUDA_CHECK(cudaGetDevice(&device));
     SB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     const size_t T = t_max, S = c.max_slots + 2;  // +prefix slot, +dummy slot
@@ -268,8 +276,11 @@ struct Engine {
     } else {
       if (dmalloc(&logits, static_cast<size_t>(logit_rows) * c.vocab)) return -1;
     }
-    // K/V tiles must hold finite values everywhere (masked P * V must stay 0).
+    // K/V tiles must hold finite values everywhere (masked P * V must stay 0); the same goes
+    // for the k/v columns of the qkv buffer, which the dense prefill attention reads in
+    // 32-row boxes that may run past the end of a sequence.
     SB_CUDA_CHECK(cudaMemsetAsync(kv_pool, 0, layer_stride * c.n_layers * sizeof(bf16), stream));
+    SB_CUDA_CHECK(cudaMemsetAsync(qkv, 0, T * qkv_dim * sizeof(bf16), stream));
     SB_CUDA_CHECK(cudaMemsetAsync(page_table, 0, S * max_pages * sizeof(int32_t), stream));
     SB_CUDA_CHECK(cudaMemsetAsync(slot_done, 0, S * sizeof(int32_t), stream));
     stage_cap = (sizeof(SeqInit) / 4) * S + static_cast<size_t>(S) * max_pages + 2 * (T / 16 + S) +
@@ -313,7 +324,19 @@ struct Engine {
                                           tok_pos, page_table, max_pages, kv_layer(l), T,
                                           c.n_q_heads, c.n_kv_heads, c.rms_eps, stream));
       }
-      if (prefill) {
+      if (prefill && fill_prefix && prefix_kv != nullptr) {
+        // the shared prefix's K/V (k|v columns of its rows) go to the dense side buffer
+        const size_t cols = 2ull * c.n_kv_heads * kHeadDim;
+        SB_CUDA_CHECK(cudaMemcpy2DAsync(prefix_kv + static_cast<size_t>(l) * prefix_rows * cols,
+                                        cols * sizeof(bf16), qkv + q_dim, qkv_dim * sizeof(bf16),
+                                        cols * sizeof(bf16), T, cudaMemcpyDeviceToDevice, stream));
+      }
+      if (prefill && prefill_tc) {
+        SB_K(SB200_KC_ATTN_PREFILL,
+             attn_prefill_dense(qkv, t_max, attn, prefix_kv, prefix_rows, c.n_layers, l, d_work,
+                                n_work, d_seq_q_start, d_seq_q_len, d_seq_past, c.n_q_heads,
+                                c.n_kv_heads, scale, stream));
+      } else if (prefill) {
         SB_K(SB200_KC_ATTN_PREFILL,
              attn_prefill(qkv, attn, kv_layer(l), page_table, max_pages, d_work, n_work,
                           d_seq_slot, d_seq_q_start, d_seq_q_len, d_seq_past, c.n_q_heads,
@@ -549,6 +572,13 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
     prefix_pages.clear();
   };
 
+  // every exit path of run() (early error returns included) hands the pages back to the
+  // engine-lifetime pool; release_all is idempotent
+  struct ReleaseGuard {
+    std::function<void()> f;
+    ~ReleaseGuard() { f(); }
+  } release_guard{release_all};
+
   // Launch one prefill step for seqs h_seqs[0..n) (page rows in h_pt), T tokens total.
   auto run_prefill = [&](int n, int T, bool sample) -> int {
     int n_work = 0;
@@ -617,7 +647,22 @@ int Engine::run(const sb200_job& job, sb200_job_stats* stats) {
     h_seqs[0] = SeqInit{prefix_slot, -1, 0, prefix_cached, 0, 0, 1, -1};
     std::fill(h_pt, h_pt + max_pages, 0);
     std::copy(prefix_pages.begin(), prefix_pages.end(), h_pt);
-    if (run_prefill(1, prefix_cached, false)) {
+    if (prefill_tc && prefix_cached > prefix_rows) {
+      cudaFree(prefix_kv);
+      prefix_kv = nullptr;
+      prefix_rows = 0;
+      const size_t n = static_cast<size_t>(c.n_layers) * prefix_cached * 2 * c.n_kv_heads * kHeadDim;
+      if (dmalloc(&prefix_kv, n)) {
+        release_all();
+        return -1;
+      }
+      prefix_rows = prefix_cached;
+      cudaMemsetAsync(prefix_kv, 0, n * sizeof(bf16), stream);
+    }
+    fill_prefix = true;
+    const int prc = run_prefill(1, prefix_cached, false);
+    fill_prefix = false;
+    if (prc) {
       release_all();
       return -1;
     }

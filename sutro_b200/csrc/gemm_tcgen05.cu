@@ -129,7 +129,8 @@ SB_DEVICE void epilogue_store(const uint32_t (&v)[32], void* __restrict__ d_out,
 // EPI_QKV_ROPE: one thread owns one token row and, per 128-column head, applies exactly
 // what rope_kv_kernel (norm_rope.cu) does to the stored bf16 tensor — bf16 rounding of the
 // projection, optional per-head RMSNorm, rotate-half RoPE with bf16 op-by-op rounding —
-// then writes q heads to the qkv buffer and k/v heads straight into the swizzled KV page.
+// then writes q heads to the qkv buffer and k/v heads straight into the swizzled KV page (and,
+// unswizzled, into their columns of the qkv buffer for the dense prefill attention).
 // The whole head lives in this thread, so the reduction needs no shuffles.
 // ---------------------------------------------------------------------------
 struct QkvRowMeta {
@@ -225,6 +226,13 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
                                  pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
     st_v4(dst_lo + ((g ^ swz) << 3), olo);
     st_v4(dst_lo + (((g + 8) ^ swz) << 3), ohi);
+    if (!is_q) {
+      // dense copy next to q: the tcgen05 prefill attention reads the new tokens' K/V from the
+      // qkv buffer through TMA (attn_prefill_tc.cu); decode reads the paged copy above
+      __nv_bfloat16* dense = qkv_out + static_cast<size_t>(row) * ldd + head * kHeadDim;
+      st_v4(dense + (g << 3), olo);
+      st_v4(dense + ((g + 8) << 3), ohi);
+    }
   }
 }
 
@@ -669,6 +677,40 @@ int make_tmap(const void* ptr, int rows, int cols, int box_rows, CUtensorMap* ou
   cache.emplace(key, *out);
   return 0;
 }
+
+}  // namespace
+
+// Generic bf16 tiled tensor map with 128-byte swizzle (rank 2..5); strides are in bytes for
+// dims 1..rank-1 (dim 0 is contiguous).  Used by the attention kernels.
+int encode_tmap_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable");
+    return -1;
+  }
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) st[i] = strides_bytes[i];
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                   const_cast<void*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(rank %d) failed: %d (ptr=%p dims=%llu,%llu box=%u,%u)",
+                   rank, static_cast<int>(r), ptr, (unsigned long long)dims[0],
+                   (unsigned long long)dims[1], box[0], box[1]);
+    return -1;
+  }
+  return 0;
+}
+
+namespace {
 
 int num_sms() {
   static int cached[64] = {0};

@@ -35,6 +35,33 @@ struct DevBuf {
   }
 };
 
+// three phases of the one-call path, timed with CUDA events on the engine's stream
+struct PhaseEvents {
+  cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t stream = nullptr;
+  bool ok = false;
+  explicit PhaseEvents(cudaStream_t s) : stream(s) {
+    ok = true;
+    for (auto& x : e) ok = ok && cudaEventCreate(&x) == cudaSuccess;
+  }
+  ~PhaseEvents() {
+    for (auto x : e)
+      if (x) cudaEventDestroy(x);
+  }
+  void mark(int i) {
+    if (ok) cudaEventRecord(e[i], stream);
+  }
+  void store(sb200_job_stats* st) {  // call after the final stream synchronisation
+    if (!st) return;
+    st->t_h2d_ms = st->t_device_ms = st->t_d2h_ms = 0.0;
+    if (!ok) return;
+    float a = 0.f, b = 0.f, c = 0.f;
+    if (cudaEventElapsedTime(&a, e[0], e[1]) == cudaSuccess) st->t_h2d_ms = a;
+    if (cudaEventElapsedTime(&b, e[1], e[2]) == cudaSuccess) st->t_device_ms = b;
+    if (cudaEventElapsedTime(&c, e[2], e[3]) == cudaSuccess) st->t_d2h_ms = c;
+  }
+};
+
 __global__ void widen_lengths_kernel(const int32_t* __restrict__ len, int64_t* __restrict__ out,
                                      int64_t n) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -51,6 +78,55 @@ __global__ void compact_rows_kernel(const int32_t* __restrict__ out_tokens, int 
   const int64_t lo = off[row], n = off[row + 1] - lo;
   const int32_t* src = out_tokens + row * stride;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) flat[lo + i] = src[i];
+}
+
+// ---- Arrow-style row selection (row sharding across GPUs and the ordered gather) ----------
+// Source row j lives in part j / part_rows (parts are equally strided blobs: what an NCCL
+// gather of padded per-rank results looks like; one part == a plain column).
+SB_DEVICE void select_src(const int64_t* __restrict__ off, int64_t part_rows, int64_t part_bytes,
+                          int64_t j, int64_t& start, int64_t& len) {
+  const int64_t part = j / part_rows, local = j - part * part_rows;
+  const int64_t* o = off + part * (part_rows + 1) + local;
+  start = part * part_bytes + o[0];
+  len = o[1] - o[0];
+}
+
+__global__ void select_lens_kernel(const int64_t* __restrict__ off, int64_t part_rows,
+                                   int64_t part_bytes, const int64_t* __restrict__ idx, int64_t m,
+                                   int64_t* __restrict__ lens) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < m) {
+    int64_t start, len;
+    select_src(off, part_rows, part_bytes, idx[i], start, len);
+    lens[i] = len;
+  }
+  if (i == m) lens[i] = 0;
+}
+
+__global__ void select_copy_kernel(const uint8_t* __restrict__ bytes,
+                                   const int64_t* __restrict__ off, int64_t part_rows,
+                                   int64_t part_bytes, const int64_t* __restrict__ idx,
+                                   const int64_t* __restrict__ out_off,
+                                   uint8_t* __restrict__ out_bytes, int64_t m) {
+  const int64_t i = blockIdx.x;
+  if (i >= m) return;
+  int64_t start, len;
+  select_src(off, part_rows, part_bytes, idx[i], start, len);
+  const uint8_t* src = bytes + start;
+  uint8_t* dst = out_bytes + out_off[i];
+  for (int64_t b = threadIdx.x; b < len; b += blockDim.x) dst[b] = src[b];
+}
+
+// exclusive scan of n int64 values with stream-ordered scratch
+int exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, cudaStream_t stream) {
+  size_t cub_bytes = 0;
+  SB_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, in, out, n, stream));
+  void* tmp = nullptr;
+  SB_CUDA_CHECK(cudaMallocAsync(&tmp, cub_bytes ? cub_bytes : 1, stream));
+  const cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, cub_bytes, in, out, n, stream);
+  cudaFreeAsync(tmp, stream);
+  SB_CUDA_CHECK(e);
+  return 0;
 }
 
 template <class T>
@@ -74,6 +150,57 @@ void sb200_result_free(sb200_result* r) {
   std::free(r->cum_logprob);
   std::free(r->embeddings);
   std::free(r);
+}
+
+// out_tokens[n_rows, stride] (row i holds len[i] tokens) -> off[n_rows+1] + flat tokens, all on
+// the device (what LocalEngine.generate hands to the detokenizer).
+int sb200_compact_rows(const int32_t* out_tokens_dev, const int32_t* out_len_dev, int64_t n_rows,
+                       int stride, int64_t* off_dev, int32_t* flat_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_rows < 0 || !off_dev || (n_rows > 0 && (!out_tokens_dev || !out_len_dev || !flat_dev))) {
+    set_last_error("compact_rows: null argument");
+    return -1;
+  }
+  const int64_t n1 = n_rows + 1;
+  int64_t* len64 = nullptr;
+  SB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&len64), n1 * 8, stream));
+  widen_lengths_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, stream>>>(
+      out_len_dev, len64, n_rows);
+  const int rc = exclusive_scan_i64(len64, off_dev, n1, stream);
+  cudaFreeAsync(len64, stream);
+  if (rc) return -1;
+  if (n_rows > 0)
+    compact_rows_kernel<<<static_cast<unsigned>(n_rows), 64, 0, stream>>>(
+        out_tokens_dev, stride, off_dev, flat_dev, n_rows);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Select m rows (idx, any order, no repeats needed) of a device-resident string column:
+// out_off[m+1] and out_bytes (capacity: the selected rows' bytes; the source size is always
+// enough).  part_rows/part_bytes describe a batch of equally strided columns (see above);
+// pass part_rows = the row count and part_bytes = 0 for a plain column.
+int sb200_rows_select(const uint8_t* bytes_dev, const int64_t* off_dev, int64_t part_rows,
+                      int64_t part_bytes, const int64_t* idx_dev, int64_t m, int64_t* out_off_dev,
+                      uint8_t* out_bytes_dev, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (m < 0 || part_rows <= 0 || !off_dev || !out_off_dev || (m > 0 && !idx_dev)) {
+    set_last_error("rows_select: bad argument");
+    return -1;
+  }
+  const int64_t m1 = m + 1;
+  int64_t* lens = nullptr;
+  SB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&lens), m1 * 8, stream));
+  select_lens_kernel<<<static_cast<unsigned>((m1 + 255) / 256), 256, 0, stream>>>(
+      off_dev, part_rows, part_bytes, idx_dev, m, lens);
+  const int rc = exclusive_scan_i64(lens, out_off_dev, m1, stream);
+  cudaFreeAsync(lens, stream);
+  if (rc) return -1;
+  if (m > 0 && out_bytes_dev != nullptr)
+    select_copy_kernel<<<static_cast<unsigned>(m), 128, 0, stream>>>(
+        bytes_dev, off_dev, part_rows, part_bytes, idx_dev, out_off_dev, out_bytes_dev, m);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 int sb200_infer_text(void* engine, void* tokenizer, const uint8_t* rows_bytes,
@@ -121,10 +248,13 @@ int sb200_infer_text(void* engine, void* tokenizer, const uint8_t* rows_bytes,
   if (d_text.alloc(n_bytes) || d_off.alloc((n_rows + 1) * 8) || d_tok.alloc(n_bytes * 4) ||
       d_toff.alloc((n_rows + 1) * 8))
     return -1;
+  PhaseEvents ev(stream);
+  ev.mark(0);
   if (n_bytes)
     SB_CUDA_CHECK(cudaMemcpyAsync(d_text.p, rows_bytes, n_bytes, cudaMemcpyHostToDevice, stream));
   SB_CUDA_CHECK(cudaMemcpyAsync(d_off.p, rows_offsets, (n_rows + 1) * 8, cudaMemcpyHostToDevice,
                                 stream));
+  ev.mark(1);  // inputs resident in HBM
   if (sb200_tokenizer_encode(tokenizer, d_text.as<uint8_t>(), n_bytes, d_off.as<int64_t>(),
                              n_rows, d_tok.as<int32_t>(), d_toff.as<int64_t>(), stream))
     return -1;
@@ -180,26 +310,24 @@ int sb200_infer_text(void* engine, void* tokenizer, const uint8_t* rows_bytes,
       set_last_error("infer_text: out of host memory");
       return -1;
     }
+    ev.mark(2);
     SB_CUDA_CHECK(cudaMemcpyAsync(r->embeddings, d_emb.p,
                                   static_cast<size_t>(n_rows) * d_model * 4,
                                   cudaMemcpyDeviceToHost, stream));
+    ev.mark(3);
     SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    ev.store(stats);
     guard.r = nullptr;
     *out = r;
     return 0;
   }
 
-  DevBuf d_len64, d_ooff, d_cub, d_flat, d_boff, d_bytes;
+  DevBuf d_len64, d_ooff, d_flat, d_boff, d_bytes;
   const int64_t n1 = n_rows + 1;
   if (d_len64.alloc(n1 * 8) || d_ooff.alloc(n1 * 8)) return -1;
   widen_lengths_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, stream>>>(
       d_len.as<int32_t>(), d_len64.as<int64_t>(), n_rows);
-  size_t cub_bytes = 0;
-  SB_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, d_len64.as<int64_t>(),
-                                              d_ooff.as<int64_t>(), n1, stream));
-  if (d_cub.alloc(cub_bytes)) return -1;
-  SB_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(d_cub.p, cub_bytes, d_len64.as<int64_t>(),
-                                              d_ooff.as<int64_t>(), n1, stream));
+  if (exclusive_scan_i64(d_len64.as<int64_t>(), d_ooff.as<int64_t>(), n1, stream)) return -1;
   r->token_offsets = host_alloc<int64_t>(n1);
   if (!r->token_offsets) {
     set_last_error("infer_text: out of host memory");
@@ -219,18 +347,14 @@ int sb200_infer_text(void* engine, void* tokenizer, const uint8_t* rows_bytes,
     set_last_error("infer_text: out of host memory");
     return -1;
   }
-  if (n_out)
-    SB_CUDA_CHECK(cudaMemcpyAsync(r->tokens, d_flat.p, n_out * 4, cudaMemcpyDeviceToHost, stream));
   if (want_logprobs) {
     r->cum_logprob = host_alloc<float>(n_rows);
     if (!r->cum_logprob) {
       set_last_error("infer_text: out of host memory");
       return -1;
     }
-    if (n_rows)
-      SB_CUDA_CHECK(cudaMemcpyAsync(r->cum_logprob, d_lp.p, n_rows * 4, cudaMemcpyDeviceToHost,
-                                    stream));
   }
+  int64_t total = 0;
   if (want_text) {
     if (d_boff.alloc(n1 * 8)) return -1;
     if (sb200_tokenizer_decode(tokenizer, d_flat.as<int32_t>(), n_out, d_ooff.as<int64_t>(),
@@ -243,7 +367,7 @@ int sb200_infer_text(void* engine, void* tokenizer, const uint8_t* rows_bytes,
     }
     SB_CUDA_CHECK(cudaMemcpyAsync(r->offsets, d_boff.p, n1 * 8, cudaMemcpyDeviceToHost, stream));
     SB_CUDA_CHECK(cudaStreamSynchronize(stream));
-    const int64_t total = r->offsets[n_rows];
+    total = r->offsets[n_rows];
     if (d_bytes.alloc(total)) return -1;
     if (sb200_tokenizer_decode(tokenizer, d_flat.as<int32_t>(), n_out, d_ooff.as<int64_t>(),
                                n_rows, d_bytes.as<uint8_t>(), d_boff.as<int64_t>(), stream))
@@ -253,10 +377,20 @@ int sb200_infer_text(void* engine, void* tokenizer, const uint8_t* rows_bytes,
       set_last_error("infer_text: out of host memory");
       return -1;
     }
-    if (total)
-      SB_CUDA_CHECK(cudaMemcpyAsync(r->bytes, d_bytes.p, total, cudaMemcpyDeviceToHost, stream));
   }
+  // results resident in HBM -> host (the two offset arrays above are sizing reads the host needs
+  // to allocate; they are part of the device phase)
+  ev.mark(2);
+  if (n_out)
+    SB_CUDA_CHECK(cudaMemcpyAsync(r->tokens, d_flat.p, n_out * 4, cudaMemcpyDeviceToHost, stream));
+  if (want_logprobs && n_rows)
+    SB_CUDA_CHECK(cudaMemcpyAsync(r->cum_logprob, d_lp.p, n_rows * 4, cudaMemcpyDeviceToHost,
+                                  stream));
+  if (want_text && total)
+    SB_CUDA_CHECK(cudaMemcpyAsync(r->bytes, d_bytes.p, total, cudaMemcpyDeviceToHost, stream));
+  ev.mark(3);
   SB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  ev.store(stats);
   guard.r = nullptr;
   *out = r;
   return 0;

@@ -3,6 +3,7 @@
 // (message retrievable through sb::last_error()).  No launcher synchronises.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -90,6 +91,20 @@ int attn_prefill_v2(const void* qkv, void* out, const void* kv_layer, const int3
                     int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
                     const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past,
                     int hq, int hkv, float scale, cudaStream_t stream);
+
+// K3 (tcgen05) — causal prefill attention over DENSE K/V: new tokens' K/V are the k/v columns
+// of the qkv buffer itself (post-norm/RoPE, written by the fused QKV epilogue), the shared
+// prefix's K/V live in prefix_kv[n_layers][prefix_rows][2*hkv*128] (K heads | V heads).
+// items: [n_items] {seq, q_tile_start} with q tile = attn_prefill_q_tile(); every sequence
+// attends to prefix rows [0, seq_past) and its own rows causally.
+int attn_prefill_dense(const void* qkv, int t_rows, void* out, const void* prefix_kv,
+                       int prefix_rows, int n_layers, int layer, const int32_t* items, int n_items,
+                       const int32_t* seq_q_start, const int32_t* seq_q_len,
+                       const int32_t* seq_past, int hq, int hkv, float scale, cudaStream_t stream);
+
+// bf16 tensor map, 128-byte swizzle, rank 2..5 (gemm_tcgen05.cu)
+int encode_tmap_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box);
 
 // K8 — FSM token-mask build, masked greedy sampling + FSM advance.
 struct SampleArgs {

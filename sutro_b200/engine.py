@@ -74,7 +74,8 @@ _STAT_INTS = ("rows_done", "input_tokens", "prefill_tokens", "decode_tokens", "p
 class JobStatsC(C.Structure):
     _fields_ = [(n, C.c_int64) for n in _STAT_INTS] + \
                [("kernel_launches", C.c_int64 * 8), ("kernel_ms", C.c_double * 8),
-                ("gemm_flops", C.c_double), ("attn_decode_bytes", C.c_double)]
+                ("gemm_flops", C.c_double), ("attn_decode_bytes", C.c_double),
+                ("t_h2d_ms", C.c_double), ("t_device_ms", C.c_double), ("t_d2h_ms", C.c_double)]
 
 
 L.register("sb200_engine_create", C.c_int, [C.POINTER(EngineConfigC), C.POINTER(EngineWeightsC),
@@ -104,6 +105,10 @@ L.register("sb200_infer_text", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c
                                          C.POINTER(JobC), C.c_int, C.c_int,
                                          C.POINTER(C.POINTER(ResultC)), C.POINTER(JobStatsC)])
 L.register("sb200_result_free", None, [C.POINTER(ResultC)])
+L.register("sb200_compact_rows", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p])
+L.register("sb200_rows_select", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p])
 
 
 def _np_ptr(a: np.ndarray, typ):
@@ -372,6 +377,161 @@ class LocalEngine:
             self._fsm_cache[key] = compile_schema(schema, limits)
         return self._fsm_cache[key]
 
+    def _job_options(self, job: "JobC", system_prompt, json_schema, max_new_tokens, ignore_eos,
+                     truncate_rows, share_prefix, fsm_limits, jump_forward, temperature, top_k,
+                     top_p, seed, seed_per_row):
+        """Fill the host-side fields of an sb200_job (prompt framing, schema automaton, jump-forward
+        plan, sampling).  Returns (dfa, plan, keep) — `keep` holds the arrays the job points at."""
+        emb_mode = self.spec.embedding_model
+        pre, suf = self._template_tokens(system_prompt)
+        dfa = self.compile_schema(json_schema, fsm_limits) if json_schema is not None else None
+        plan = None
+        if dfa is not None and jump_forward and not emb_mode:
+            # jump-forward decoding: bytes the automaton forces are not the model's choice —
+            # the forced output prefix rides with the prompt, forced terminal tails are
+            # appended by the sampler without another forward pass
+            plan = self._jump_plan(dfa, (id(dfa),))
+            if plan is not None and len(plan["prefix_tokens"]) >= max_new_tokens:
+                plan = None
+        if plan is not None:
+            suf = np.concatenate([suf, plan["prefix_tokens"]]).astype(np.int32)
+        job.prefix_tokens, job.n_prefix = _np_ptr(pre, c_i32p), len(pre)
+        job.suffix_tokens, job.n_suffix = _np_ptr(suf, c_i32p), len(suf)
+        job.share_prefix, job.max_new_tokens = int(share_prefix), max_new_tokens
+        job.ignore_eos, job.truncate_rows = int(ignore_eos), int(truncate_rows)
+        if dfa is not None:
+            job.fsm_trans = _np_ptr(dfa.trans, c_i32p)
+            job.fsm_accept = _np_ptr(dfa.accept, c_u8p)
+            job.fsm_final = _np_ptr(dfa.final, c_u8p)
+            job.fsm_states, job.fsm_start = dfa.n_states, dfa.start
+            if plan is not None:
+                job.fsm_start = plan["start"]
+                job.n_forced_prefix = len(plan["prefix_tokens"])
+                job.fsm_tail_off = _np_ptr(plan["tail_off"], c_i32p)
+                job.fsm_tail_tok = _np_ptr(plan["tail_tok"], c_i32p)
+        job.temperature, job.top_k, job.top_p = float(temperature), int(top_k), float(top_p)
+        job.seed, job.seed_per_row = int(seed) & (2 ** 64 - 1), int(seed_per_row)
+        return dfa, plan, (pre, suf)
+
+    def run_blob_dev(self, d_text: torch.Tensor, d_off: torch.Tensor, n_rows: int, n_bytes: int,
+                     system_prompt: Optional[str] = None,
+                     json_schema: Optional[Dict[str, Any]] = None, max_new_tokens: int = 64,
+                     ignore_eos: bool = False, truncate_rows: bool = True,
+                     share_prefix: bool = True, fsm_limits: Optional[FsmLimits] = None,
+                     progress: Optional[Callable[[int, int, int], None]] = None,
+                     return_text: bool = True, profile: bool = False,
+                     return_first_logits: bool = False, jump_forward: bool = True,
+                     temperature: float = 0.0, top_k: int = 0, top_p: float = 1.0, seed: int = 0,
+                     seed_per_row: bool = False, return_logprobs: bool = False,
+                     row_ids: Optional[Sequence[int]] = None) -> Dict[str, Any]:
+        """Phase B of the hot path, HBM to HBM: a device-resident Arrow column (uint8 bytes +
+        int64 offsets[n_rows+1]) -> tokenise -> prefill/decode (+mask) -> detokenise ->
+        device-resident results (`d_bytes`/`d_boff`, `flat`/`ooff` tokens, `d_emb`, ...).
+        Used by generate() and by the row-sharded multi-GPU path (sharding.py), which moves
+        these buffers between ranks over NCCL."""
+        dev = self.device
+        emb_mode = self.spec.embedding_model
+        lib = L.lib()
+        with torch.cuda.device(dev):
+            d_tok = torch.empty(max(n_bytes, 1), dtype=torch.int32, device=dev)
+            d_toff = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+            L.check(lib.sb200_tokenizer_encode(self.tokenizer._h, d_text.data_ptr(), n_bytes,
+                                               d_off.data_ptr(), n_rows, d_tok.data_ptr(),
+                                               d_toff.data_ptr(), L.current_stream()))
+            toff = d_toff.cpu().numpy()          # the scheduler needs row lengths on the host
+            d_out = d_len = d_emb = None
+            if emb_mode:
+                d_emb = torch.empty(n_rows, self.spec.d_model, dtype=torch.float32, device=dev)
+            else:
+                d_out = torch.empty(n_rows, max_new_tokens, dtype=torch.int32, device=dev)
+                d_len = torch.zeros(n_rows, dtype=torch.int32, device=dev)
+            cb = PROGRESS_FN(lambda r, i, o, u: progress(r, i, o)) if progress else PROGRESS_FN()
+            job = JobC()
+            dfa, plan, keep = self._job_options(job, system_prompt, json_schema, max_new_tokens,
+                                                ignore_eos, truncate_rows, share_prefix, fsm_limits,
+                                                jump_forward, temperature, top_k, top_p, seed,
+                                                seed_per_row)
+            job.row_tokens_dev, job.row_tok_off_dev = d_tok.data_ptr(), d_toff.data_ptr()
+            job.row_tok_off, job.n_rows = _np_ptr(toff, c_i64p), n_rows
+            job.out_tokens_dev = L.ptr(d_out)
+            job.out_len_dev = L.ptr(d_len)
+            job.out_embed_dev = L.ptr(d_emb)
+            job.progress = cb
+            job.profile = int(profile)
+            d_first = None
+            if return_first_logits and not emb_mode:
+                d_first = torch.zeros(n_rows, self.spec.vocab_size, dtype=torch.float32, device=dev)
+                job.out_first_logits_dev = d_first.data_ptr()
+            d_ids = None
+            if row_ids is not None and seed_per_row:
+                # rows of a sharded job keep the Philox stream of their index in the whole job
+                ids = np.ascontiguousarray(row_ids, dtype=np.int64)
+                if ids.shape != (n_rows,):
+                    raise ValueError("row_ids must hold one id per row")
+                d_ids = torch.from_numpy(ids).to(dev)
+                job.row_ids_dev = d_ids.data_ptr()
+            d_lp = None
+            if return_logprobs and not emb_mode:
+                d_lp = torch.zeros(n_rows, dtype=torch.float32, device=dev)
+                job.out_cum_logprob_dev = d_lp.data_ptr()
+            st = JobStatsC()
+            torch.cuda.synchronize(dev)
+            t_tok = time.perf_counter()
+            L.check(lib.sb200_engine_run(self._h, C.byref(job), C.byref(st)))
+            t_run = time.perf_counter()
+            n_out = 0
+            d_bytes = d_boff = flat = ooff = None
+            if not emb_mode:
+                # compaction of the [n_rows, max_new] token matrix: native kernels, no tensor ops
+                ooff = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+                flat = torch.empty(max(n_rows * max_new_tokens, 1), dtype=torch.int32, device=dev)
+                L.check(lib.sb200_compact_rows(d_out.data_ptr(), d_len.data_ptr(), n_rows,
+                                               max_new_tokens, ooff.data_ptr(), flat.data_ptr(),
+                                               L.current_stream()))
+                n_out = int(ooff[-1].item())
+                flat = flat[:n_out]
+                if return_text:
+                    d_boff = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+                    L.check(lib.sb200_tokenizer_decode(self.tokenizer._h, flat.data_ptr(), n_out,
+                                                       ooff.data_ptr(), n_rows, None,
+                                                       d_boff.data_ptr(), L.current_stream()))
+                    total = int(d_boff[-1].item())
+                    d_bytes = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+                    L.check(lib.sb200_tokenizer_decode(self.tokenizer._h, flat.data_ptr(), n_out,
+                                                       ooff.data_ptr(), n_rows,
+                                                       d_bytes.data_ptr(), d_boff.data_ptr(),
+                                                       L.current_stream()))
+                    d_bytes = d_bytes[:total]
+            torch.cuda.synchronize(dev)
+        stats = {k: int(getattr(st, k)) for k in _STAT_INTS}
+        stats["kernel_launches"] = dict(zip(KERNEL_CLASSES, list(st.kernel_launches)))
+        stats["kernel_ms"] = dict(zip(KERNEL_CLASSES, list(st.kernel_ms)))
+        stats["gemm_flops"], stats["attn_decode_bytes"] = st.gemm_flops, st.attn_decode_bytes
+        # my kernels outside the engine: tokenizer encode (4), compaction (widen + scan + compact)
+        # and decode (2 passes: 2 + 3)
+        stats["tokenizer_launches"] = 4 + (0 if emb_mode else 3) + \
+            (5 if (return_text and not emb_mode) else 0)
+        stats.update(output_tokens=n_out, n_rows=n_rows, t_engine_s=t_run - t_tok,
+                     fsm_states=0 if dfa is None else dfa.n_states, jump_forward=plan is not None,
+                     forced_prefix_tokens=0 if plan is None else int(len(plan["prefix_tokens"])))
+        return dict(d_bytes=d_bytes, d_boff=d_boff, flat=flat, ooff=ooff, d_emb=d_emb,
+                    d_first=d_first, d_lp=d_lp, stats=stats, t_tok=t_tok, t_run=t_run)
+
+    def rows_select(self, d_bytes: torch.Tensor, d_off: torch.Tensor, part_rows: int,
+                    part_bytes: int, d_idx: torch.Tensor, capacity: int):
+        """Device-side Arrow row selection (sb200_rows_select): rows `d_idx` of the resident
+        column (or batch of equally strided columns) -> (offsets[m+1], bytes[capacity])."""
+        m = int(d_idx.numel())
+        dev = self.device
+        with torch.cuda.device(dev):
+            out_off = torch.empty(m + 1, dtype=torch.int64, device=dev)
+            out_bytes = torch.empty(max(int(capacity), 1), dtype=torch.uint8, device=dev)
+            L.check(L.lib().sb200_rows_select(d_bytes.data_ptr(), d_off.data_ptr(), int(part_rows),
+                                              int(part_bytes), d_idx.data_ptr(), m,
+                                              out_off.data_ptr(), out_bytes.data_ptr(),
+                                              L.current_stream()))
+        return out_off, out_bytes
+
     def generate(self, rows, system_prompt: Optional[str] = None,
                  json_schema: Optional[Dict[str, Any]] = None, max_new_tokens: int = 64,
                  ignore_eos: bool = False, truncate_rows: bool = True, share_prefix: bool = True,
@@ -402,18 +562,10 @@ class LocalEngine:
                                     np.zeros((0, self.spec.d_model), np.float32) if emb_mode
                                     else None, {"n_rows": 0, "input_tokens": 0,
                                                 "output_tokens": 0, "rows_done": 0})
-        pre, suf = self._template_tokens(system_prompt)
-        dfa = self.compile_schema(json_schema, fsm_limits) if json_schema is not None else None
-        plan = None
-        if dfa is not None and jump_forward and not emb_mode:
-            # jump-forward decoding: bytes the automaton forces are not the model's choice —
-            # the forced output prefix rides with the prompt, forced terminal tails are
-            # appended by the sampler without another forward pass
-            plan = self._jump_plan(dfa, (id(dfa),))
-            if plan is not None and len(plan["prefix_tokens"]) >= max_new_tokens:
-                plan = None
-        if plan is not None:
-            suf = np.concatenate([suf, plan["prefix_tokens"]]).astype(np.int32)
+        # template / schema compilation (cached) belongs to the host phase
+        self._template_tokens(system_prompt)
+        if json_schema is not None:
+            self.compile_schema(json_schema, fsm_limits)
         with torch.cuda.device(dev):
             d_text = (torch.from_numpy(np.ascontiguousarray(data)).to(dev) if n_bytes
                       else torch.zeros(1, dtype=torch.uint8, device=dev))
@@ -421,119 +573,40 @@ class LocalEngine:
             torch.cuda.synchronize(dev)
             t_a = time.perf_counter()
             # ---- phase B ---------------------------------------------------------
-            d_tok = torch.empty(max(n_bytes, 1), dtype=torch.int32, device=dev)
-            d_toff = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
-            lib = L.lib()
-            L.check(lib.sb200_tokenizer_encode(self.tokenizer._h, d_text.data_ptr(), n_bytes,
-                                               d_off.data_ptr(), n_rows, d_tok.data_ptr(),
-                                               d_toff.data_ptr(), L.current_stream()))
-            toff = d_toff.cpu().numpy()          # the scheduler needs row lengths on the host
-            d_out = d_len = d_emb = None
-            if emb_mode:
-                d_emb = torch.empty(n_rows, self.spec.d_model, dtype=torch.float32, device=dev)
-            else:
-                d_out = torch.empty(n_rows, max_new_tokens, dtype=torch.int32, device=dev)
-                d_len = torch.zeros(n_rows, dtype=torch.int32, device=dev)
-            cb = PROGRESS_FN(lambda r, i, o, u: progress(r, i, o)) if progress else PROGRESS_FN()
-            job = JobC()
-            job.row_tokens_dev, job.row_tok_off_dev = d_tok.data_ptr(), d_toff.data_ptr()
-            job.row_tok_off, job.n_rows = _np_ptr(toff, c_i64p), n_rows
-            job.prefix_tokens, job.n_prefix = _np_ptr(pre, c_i32p), len(pre)
-            job.suffix_tokens, job.n_suffix = _np_ptr(suf, c_i32p), len(suf)
-            job.share_prefix, job.max_new_tokens = int(share_prefix), max_new_tokens
-            job.ignore_eos, job.truncate_rows = int(ignore_eos), int(truncate_rows)
-            if dfa is not None:
-                job.fsm_trans = _np_ptr(dfa.trans, c_i32p)
-                job.fsm_accept = _np_ptr(dfa.accept, c_u8p)
-                job.fsm_final = _np_ptr(dfa.final, c_u8p)
-                job.fsm_states, job.fsm_start = dfa.n_states, dfa.start
-                if plan is not None:
-                    job.fsm_start = plan["start"]
-                    job.n_forced_prefix = len(plan["prefix_tokens"])
-                    job.fsm_tail_off = _np_ptr(plan["tail_off"], c_i32p)
-                    job.fsm_tail_tok = _np_ptr(plan["tail_tok"], c_i32p)
-            job.out_tokens_dev = L.ptr(d_out)
-            job.out_len_dev = L.ptr(d_len)
-            job.out_embed_dev = L.ptr(d_emb)
-            job.progress = cb
-            job.profile = int(profile)
-            d_first = None
-            if return_first_logits and not emb_mode:
-                d_first = torch.zeros(n_rows, self.spec.vocab_size, dtype=torch.float32, device=dev)
-                job.out_first_logits_dev = d_first.data_ptr()
-            job.temperature, job.top_k, job.top_p = float(temperature), int(top_k), float(top_p)
-            job.seed, job.seed_per_row = int(seed) & (2 ** 64 - 1), int(seed_per_row)
-            d_ids = None
-            if row_ids is not None and seed_per_row:
-                # rows of a sharded job keep the Philox stream of their index in the whole job
-                ids = np.ascontiguousarray(row_ids, dtype=np.int64)
-                if ids.shape != (n_rows,):
-                    raise ValueError("row_ids must hold one id per row")
-                d_ids = torch.from_numpy(ids).to(dev)
-                job.row_ids_dev = d_ids.data_ptr()
-            d_lp = None
-            if return_logprobs and not emb_mode:
-                d_lp = torch.zeros(n_rows, dtype=torch.float32, device=dev)
-                job.out_cum_logprob_dev = d_lp.data_ptr()
-            st = JobStatsC()
-            torch.cuda.synchronize(dev)
-            t_tok = time.perf_counter()
-            L.check(lib.sb200_engine_run(self._h, C.byref(job), C.byref(st)))
-            t_run = time.perf_counter()
-            n_out = d2h = 0
-            d_bytes = d_boff = flat = ooff = None
-            if not emb_mode:
-                lens = d_len.to(torch.int64)
-                ooff = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
-                torch.cumsum(lens, 0, out=ooff[1:])
-                keep = torch.arange(max_new_tokens, device=dev)[None, :] < lens[:, None]
-                flat = d_out[keep].contiguous()
-                n_out = int(flat.numel())
-                if return_text:
-                    d_boff = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
-                    L.check(lib.sb200_tokenizer_decode(self.tokenizer._h, flat.data_ptr(), n_out,
-                                                       ooff.data_ptr(), n_rows, None,
-                                                       d_boff.data_ptr(), L.current_stream()))
-                    total = int(d_boff[-1].item())
-                    d_bytes = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
-                    L.check(lib.sb200_tokenizer_decode(self.tokenizer._h, flat.data_ptr(), n_out,
-                                                       ooff.data_ptr(), n_rows,
-                                                       d_bytes.data_ptr(), d_boff.data_ptr(),
-                                                       L.current_stream()))
-                    d_bytes = d_bytes[:total]
-            torch.cuda.synchronize(dev)
+            r = self.run_blob_dev(d_text, d_off, n_rows, n_bytes, system_prompt=system_prompt,
+                                  json_schema=json_schema, max_new_tokens=max_new_tokens,
+                                  ignore_eos=ignore_eos, truncate_rows=truncate_rows,
+                                  share_prefix=share_prefix, fsm_limits=fsm_limits,
+                                  progress=progress, return_text=return_text, profile=profile,
+                                  return_first_logits=return_first_logits,
+                                  jump_forward=jump_forward, temperature=temperature, top_k=top_k,
+                                  top_p=top_p, seed=seed, seed_per_row=seed_per_row,
+                                  return_logprobs=return_logprobs, row_ids=row_ids)
             t_b = time.perf_counter()
             # ---- phase C ---------------------------------------------------------
             outputs = out_tokens = emb = None
+            d2h = 0
             if emb_mode:
-                emb = d_emb.cpu().numpy()
+                emb = r["d_emb"].cpu().numpy()
                 d2h = emb.nbytes
             else:
                 if return_text:
-                    b, boff = d_bytes.cpu().numpy(), d_boff.cpu().numpy()
+                    b, boff = r["d_bytes"].cpu().numpy(), r["d_boff"].cpu().numpy()
                     d2h += b.nbytes + boff.nbytes
                     outputs = blob_to_rows(b, boff)
                 if return_tokens:
-                    fl, oo = flat.cpu().numpy(), ooff.cpu().numpy()
+                    fl, oo = r["flat"].cpu().numpy(), r["ooff"].cpu().numpy()
                     d2h += fl.nbytes + oo.nbytes
                     out_tokens = [fl[oo[i]:oo[i + 1]].tolist() for i in range(n_rows)]
             t_end = time.perf_counter()
-        stats = {k: int(getattr(st, k)) for k in _STAT_INTS}
-        stats["kernel_launches"] = dict(zip(KERNEL_CLASSES, list(st.kernel_launches)))
-        stats["kernel_ms"] = dict(zip(KERNEL_CLASSES, list(st.kernel_ms)))
-        stats["gemm_flops"], stats["attn_decode_bytes"] = st.gemm_flops, st.attn_decode_bytes
-        # my kernels outside the engine: tokenizer encode (4) and decode (2 passes: 2 + 3)
-        stats["tokenizer_launches"] = 4 + (5 if (return_text and not emb_mode) else 0)
-        stats.update(output_tokens=n_out, n_rows=n_rows,
-                     h2d_bytes=int(data.nbytes + off.nbytes), d2h_bytes=int(d2h),
-                     t_h2d_s=t_a - t0, t_tokenize_s=t_tok - t_a, t_engine_s=t_run - t_tok,
-                     t_detok_s=t_b - t_run, t_device_s=t_b - t_a, t_d2h_s=t_end - t_b,
-                     t_total_s=t_end - t0, fsm_states=0 if dfa is None else dfa.n_states,
-                     jump_forward=plan is not None,
-                     forced_prefix_tokens=0 if plan is None else int(len(plan["prefix_tokens"])))
+        stats = r["stats"]
+        stats.update(h2d_bytes=int(data.nbytes + off.nbytes), d2h_bytes=int(d2h),
+                     t_h2d_s=t_a - t0, t_tokenize_s=r["t_tok"] - t_a,
+                     t_detok_s=t_b - r["t_run"], t_device_s=t_b - t_a, t_d2h_s=t_end - t_b,
+                     t_total_s=t_end - t0)
         return GenerationResult(outputs, out_tokens, emb, stats,
-                                None if d_first is None else d_first.cpu(),
-                                None if d_lp is None else d_lp.cpu().numpy())
+                                None if r["d_first"] is None else r["d_first"].cpu(),
+                                None if r["d_lp"] is None else r["d_lp"].cpu().numpy())
 
 
 def _infer_one_call(self, rows, system_prompt: Optional[str] = None,
@@ -542,69 +615,70 @@ def _infer_one_call(self, rows, system_prompt: Optional[str] = None,
                     share_prefix: bool = True, fsm_limits: Optional[FsmLimits] = None,
                     jump_forward: bool = True, temperature: float = 0.0, top_k: int = 0,
                     top_p: float = 1.0, seed: int = 0, seed_per_row: bool = False,
-                    return_logprobs: bool = False) -> GenerationResult:
+                    return_logprobs: bool = False, return_tokens: bool = True,
+                    progress: Optional[Callable[[int, int, int], None]] = None,
+                    profile: bool = False) -> GenerationResult:
     """The same job through `sb200_infer_text`: ONE C-ABI call with host buffers in and out
-    (what a non-Python host would bind).  `generate` is the phased form of the same work —
-    it keeps the phases apart so that the benchmark can time them; the results are identical."""
+    (what a non-Python host would bind; the SDK's infer() and bench.py's `e2e` use it).
+    `generate` is the phased form of the same work; the results are identical.  The call times
+    its three phases with CUDA events on the engine's stream: stats["t_h2d_ms"] (rows -> HBM),
+    stats["t_device_ms"] (tokenise -> prefill/decode -> detokenise, HBM to HBM) and
+    stats["t_d2h_ms"]."""
     if self.vocab.normalize_nfc:
         rows = _nfc_rows(rows)
+    t0 = time.perf_counter()
     data, off = rows_to_blob(rows)
     n_rows = len(off) - 1
     emb_mode = self.spec.embedding_model
-    pre, suf = self._template_tokens(system_prompt)
-    dfa = self.compile_schema(json_schema, fsm_limits) if json_schema is not None else None
-    plan = None
-    if dfa is not None and jump_forward and not emb_mode:
-        plan = self._jump_plan(dfa, (id(dfa),))
-        if plan is not None and len(plan["prefix_tokens"]) >= max_new_tokens:
-            plan = None
-    if plan is not None:
-        suf = np.concatenate([suf, plan["prefix_tokens"]]).astype(np.int32)
     data, off = np.ascontiguousarray(data), np.ascontiguousarray(off, dtype=np.int64)
     job = JobC()
-    job.prefix_tokens, job.n_prefix = _np_ptr(pre, c_i32p), len(pre)
-    job.suffix_tokens, job.n_suffix = _np_ptr(suf, c_i32p), len(suf)
-    job.share_prefix, job.max_new_tokens = int(share_prefix), max_new_tokens
-    job.ignore_eos, job.truncate_rows = int(ignore_eos), int(truncate_rows)
-    if dfa is not None:
-        job.fsm_trans = _np_ptr(dfa.trans, c_i32p)
-        job.fsm_accept = _np_ptr(dfa.accept, c_u8p)
-        job.fsm_final = _np_ptr(dfa.final, c_u8p)
-        job.fsm_states, job.fsm_start = dfa.n_states, dfa.start
-        if plan is not None:
-            job.fsm_start = plan["start"]
-            job.n_forced_prefix = len(plan["prefix_tokens"])
-            job.fsm_tail_off = _np_ptr(plan["tail_off"], c_i32p)
-            job.fsm_tail_tok = _np_ptr(plan["tail_tok"], c_i32p)
-    job.temperature, job.top_k, job.top_p = float(temperature), int(top_k), float(top_p)
-    job.seed, job.seed_per_row = int(seed) & (2 ** 64 - 1), int(seed_per_row)
+    dfa, plan, keep = self._job_options(job, system_prompt, json_schema, max_new_tokens,
+                                        ignore_eos, truncate_rows, share_prefix, fsm_limits,
+                                        jump_forward, temperature, top_k, top_p, seed, seed_per_row)
+    cb = PROGRESS_FN(lambda r, i, o, u: progress(r, i, o)) if progress else PROGRESS_FN()
+    job.progress = cb
+    job.profile = int(profile)
     st, res = JobStatsC(), C.POINTER(ResultC)()
-    t0 = time.perf_counter()
+    t1 = time.perf_counter()
     L.check(L.lib().sb200_infer_text(self._h, self.tokenizer._h, data.ctypes.data, off.ctypes.data,
                                      n_rows, C.byref(job), 1, int(return_logprobs),
                                      C.byref(res), C.byref(st)))
+    t2 = time.perf_counter()
+    n_out = d2h = 0
     try:
         r = res.contents
         outputs = out_tokens = emb = lp = None
         if emb_mode:
             emb = np.ctypeslib.as_array(r.embeddings, shape=(n_rows, r.d_model)).copy() \
                 if n_rows else np.zeros((0, self.spec.d_model), np.float32)
+            d2h = emb.nbytes
         else:
             toff = np.ctypeslib.as_array(r.token_offsets, shape=(n_rows + 1,)).copy()
-            toks = (np.ctypeslib.as_array(r.tokens, shape=(int(toff[-1]),)).copy()
-                    if toff[-1] else np.zeros(0, np.int32))
-            out_tokens = [toks[toff[i]:toff[i + 1]].tolist() for i in range(n_rows)]
+            n_out = int(toff[-1])
+            if return_tokens:
+                toks = (np.ctypeslib.as_array(r.tokens, shape=(n_out,)).copy()
+                        if n_out else np.zeros(0, np.int32))
+                out_tokens = [toks[toff[i]:toff[i + 1]].tolist() for i in range(n_rows)]
             boff = np.ctypeslib.as_array(r.offsets, shape=(n_rows + 1,)).copy()
             blob = (np.ctypeslib.as_array(r.bytes, shape=(int(boff[-1]),)).copy()
                     if boff[-1] else np.zeros(0, np.uint8))
             outputs = blob_to_rows(blob, boff)
+            d2h = int(blob.nbytes + boff.nbytes + toff.nbytes + 4 * n_out)
             if return_logprobs and n_rows:
                 lp = np.ctypeslib.as_array(r.cum_logprob, shape=(n_rows,)).copy()
     finally:
         L.lib().sb200_result_free(res)
     stats = {k: int(getattr(st, k)) for k in _STAT_INTS}
-    stats.update(n_rows=n_rows, t_total_s=time.perf_counter() - t0,
-                 output_tokens=0 if out_tokens is None else sum(map(len, out_tokens)))
+    stats["kernel_launches"] = dict(zip(KERNEL_CLASSES, list(st.kernel_launches)))
+    stats["kernel_ms"] = dict(zip(KERNEL_CLASSES, list(st.kernel_ms)))
+    stats["gemm_flops"], stats["attn_decode_bytes"] = st.gemm_flops, st.attn_decode_bytes
+    stats["tokenizer_launches"] = 4 + (0 if emb_mode else 3 + 5)
+    stats.update(n_rows=n_rows, output_tokens=n_out, t_total_s=time.perf_counter() - t0,
+                 t_call_s=t2 - t1, t_h2d_ms=st.t_h2d_ms, t_device_ms=st.t_device_ms,
+                 t_d2h_ms=st.t_d2h_ms, t_device_s=st.t_device_ms * 1e-3,
+                 h2d_bytes=int(data.nbytes + off.nbytes), d2h_bytes=int(d2h),
+                 fsm_states=0 if dfa is None else dfa.n_states, jump_forward=plan is not None,
+                 forced_prefix_tokens=0 if plan is None else int(len(plan["prefix_tokens"])))
     return GenerationResult(outputs, out_tokens, emb, stats, None, lp)
 
 

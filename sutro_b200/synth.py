@@ -79,11 +79,13 @@ def corpus_sentences(n: int, seed: int) -> List[str]:
 
 
 def product_reviews(n: int, seed: int = 0) -> List[str]:
-    """Config 2: product reviews, lognormal length (clipped), mean ~ 90-100 tokens."""
+    """Config 2: product reviews, length ~ lognormal, clipped to roughly
+    16-256 tokens, mean ~ 96 tokens under the synthetic BPE vocabulary (a sentence of the
+    phrase grammar is ~9.4 tokens; measured by tests/test_bench_cpu.py)."""
     rng = np.random.RandomState(seed)
     out = []
     for _ in range(n):
-        sents = int(np.clip(np.round(rng.lognormal(mean=1.6, sigma=0.5)), 1, 14))
+        sents = int(np.clip(np.round(rng.lognormal(mean=2.2, sigma=0.5)), 2, 27))
         out.append(_review(rng, sents))
     return out
 

@@ -6,9 +6,10 @@ Tolerances (stated once, used below):
   MARGIN_EPS   a greedy decision must equal the oracle's whenever the oracle's top-1/top-2
                logit gap exceeds 0.06 (logit std is ~1; two bf16 pipelines that differ only
                in fp32 summation order disagree by ~0.02 on these tiny models).  Below that
-               gap the engine may pick the oracle's runner-up instead (a near-tie flip);
-               anything else fails.  After a flip the sequences legitimately diverge, so
-               the comparison stops there.
+               gap the engine may pick another token whose oracle logit is within 0.06 of the
+               oracle's best (a near-tie flip); anything else fails.  After a flip the
+               sequences legitimately diverge, so the comparison stops there.  Every flip is
+               recorded (FLIP_LOG) and the counts are printed and bounded per test.
   EMB_TOL      embedding vectors: max abs diff 2e-2 on unit-norm vectors.
 """
 import json
@@ -65,10 +66,40 @@ def compare_greedy(got: List[int], ref, label="", eos_id=-1):
         assert i in dec, (label, "forced token differs", i, got, ref.tokens)
         d = dec[i]
         assert ref.margins[d] < MARGIN_EPS, (label, i, got, ref.tokens, ref.margins)
-        assert have == ref.runner_up[d], (label, i, have, ref.runner_up[d])
+        # the engine's pick must itself be within the near-tie band of the oracle's best
+        # (several candidates can sit inside it at once)
+        gap = ref.near[d].get(have)
+        assert gap is not None and gap < MARGIN_EPS, (label, i, have, ref.near[d])
+        FLIP_LOG.append((label, round(ref.margins[d], 4), round(gap, 4)))
         return d, len(ref.margins), 1
     return len(ref.margins), len(ref.margins), 0
 
+
+FLIP_LOG = []     # (row, oracle top-1 margin, oracle gap of the engine's pick) of every near-tie flip
+
+
+def record_parity(test: str, rows: int, compared: int, total: int, flips: int):
+    """One line per parity test run: how many greedy decisions were checked against the oracle
+    and how many near-tie flips were seen (appended to gpurun_out/parity_flips.jsonl so that
+    the numbers behind the tolerance travel back from the GPU box; also printed)."""
+    import os
+    rec = {"test": test, "rows": rows, "decisions_verified": compared, "decisions_total": total,
+           "near_tie_flips": flips, "margin_eps": MARGIN_EPS,
+           "flips": [list(f) for f in FLIP_LOG[-flips:]] if flips else []}
+    print("PARITY", json.dumps(rec))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_flips.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except OSError:
+        pass
+
+
+# rows (of 15) allowed to hit a near-tie flip within their first 12 decisions; measured counts
+# are in profiles/r02_parity_flips.jsonl (seeded tiny random models have flat logits: a 12-token
+# greedy run crosses a < 0.06 margin in roughly one row out of three)
+MAX_FLIP_ROWS = 7
 
 ROWS = synth.README_REVIEWS + synth.product_reviews(9, seed=7) + ["", "x", "ok ok ok"]
 
@@ -108,8 +139,9 @@ def test_unconstrained_greedy_matches_oracle(name):
         assert len(got) == 12
         c, t, f = compare_greedy(got, r, row[:30], v.eos_id)
         compared, total, flips = compared + c, total + t, flips + f
+    record_parity(f"unconstrained_greedy[{name}]", len(ROWS), compared, total, flips)
     assert compared >= 0.5 * total, (compared, total)   # the criterion is not vacuous
-    assert flips <= len(ROWS) * 2 // 3, flips
+    assert flips <= MAX_FLIP_ROWS, flips
     assert res.stats["rows_done"] == len(ROWS)
     assert res.stats["prefix_cached_tokens"] >= 16       # the system prompt was shared
 
@@ -182,8 +214,9 @@ def test_schema_constrained_outputs_validate_and_match_oracle(schema_model, jump
         r = model.generate(ref_tok.render(tpl, row, max_prompt), 64, v.eos_id, fsm=fsm)
         c, t, f = compare_greedy(got, r, row[:30], v.eos_id)
         compared, total, flips = compared + c, total + t, flips + f
+    record_parity(f"schema[{schema_model.__name__},jump={jump}]", len(ROWS), compared, total, flips)
     assert compared >= 0.5 * total, (compared, total)
-    assert flips <= len(ROWS) * 2 // 3, flips
+    assert flips <= MAX_FLIP_ROWS, flips
     if jump:  # fewer forward passes: the sentiment rows need 1-2 decisions each
         assert res.stats["decode_tokens"] < sum(len(t) for t in res.out_tokens)
 

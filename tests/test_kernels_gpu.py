@@ -367,6 +367,114 @@ def test_attn_prefill(hq, hkv):
             assert torch.allclose(got, ref, rtol=2e-2, atol=2e-2), (i, j, (got - ref).abs().max())
 
 
+def _dense_case(hq, hkv, specs, prefix_rows, n_layers, layer, seed, q_gain=1.0, t_pad=7):
+    """Random dense qkv / prefix buffers + the (items, q_start, q_len, past) arrays of
+    sb200_attn_prefill_dense.  specs: [(past, new)] per sequence."""
+    torch.manual_seed(seed)
+    T = sum(q for _, q in specs)
+    ldq = (hq + 2 * hkv) * KV.HD
+    qkv = bf(torch.randn(T + t_pad, ldq, device=DEV))
+    qkv[:, :hq * KV.HD] *= q_gain
+    pre = bf(torch.randn(n_layers, max(prefix_rows, 1), 2 * hkv * KV.HD, device=DEV))
+    qt = L.lib().sb200_attn_prefill_q_tile(hq, hkv)
+    q_start, items, acc = [], [], 0
+    for i, (p, q) in enumerate(specs):
+        q_start.append(acc)
+        acc += q
+        for t0 in range(0, q, qt):
+            items += [i, t0]
+    return qkv, pre, q_start, items, T
+
+
+def _dense_ref(qkv, pre, layer, hq, hkv, specs, q_start, scale):
+    """fp32 reference of the dense prefill attention: [T, hq, 128]."""
+    out = []
+    for i, (p, q) in enumerate(specs):
+        rows = qkv[q_start[i]:q_start[i] + q].view(q, hq + 2 * hkv, KV.HD)
+        kown, vown = rows[:, hq:hq + hkv], rows[:, hq + hkv:]
+        pk = pre[layer, :p, :hkv * KV.HD].view(p, hkv, KV.HD)
+        pv = pre[layer, :p, hkv * KV.HD:].view(p, hkv, KV.HD)
+        k = torch.cat([pk, kown]).float().repeat_interleave(hq // hkv, dim=1)   # [p+q, hq, 128]
+        v = torch.cat([pv, vown]).float().repeat_interleave(hq // hkv, dim=1)
+        s = torch.einsum("qhd,lhd->hql", rows[:, :hq].float(), k) * scale       # [hq, q, p+q]
+        pos_q = torch.arange(q, device=DEV)[:, None] + p
+        pos_k = torch.arange(p + q, device=DEV)[None, :]
+        s = s.masked_fill(pos_k > pos_q, float("-inf"))
+        out.append(torch.einsum("hql,lhd->qhd", torch.softmax(s, dim=-1), v))
+    return torch.cat(out)
+
+
+@pytest.mark.parametrize("hq,hkv", [(32, 8), (16, 8), (4, 4), (16, 2)])
+def test_attn_prefill_dense_tcgen05(hq, hkv):
+    """K3 on tcgen05: new tokens attend to [dense shared prefix | own rows] (TMA-fed UMMA,
+    S/O in TMEM) — against an fp32 softmax(QK^T)V over the same bf16 inputs."""
+    specs = [(0, 1), (0, 16), (0, 17), (0, 100), (32, 5), (32, 70), (48, 200), (3, 33),
+             (46, 111), (130, 140), (200, 300), (0, 129), (1, 128)]
+    n_layers, layer, prefix_rows = 3, 1, 200
+    qkv, pre, q_start, items, T = _dense_case(hq, hkv, specs, prefix_rows, n_layers, layer,
+                                              seed=hq * 7 + hkv)
+    out = torch.zeros(T, hq * KV.HD, dtype=torch.bfloat16, device=DEV)
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
+    scale = 1.0 / math.sqrt(KV.HD)
+    d_items, d_qs = i32(items), i32(q_start)
+    d_ql, d_past = i32([q for _, q in specs]), i32([p for p, _ in specs])
+    L.check(L.lib().sb200_attn_prefill_dense(
+        L.ptr(qkv), qkv.shape[0], L.ptr(out), L.ptr(pre), prefix_rows, n_layers, layer,
+        L.ptr(d_items), len(items) // 2, L.ptr(d_qs), L.ptr(d_ql), L.ptr(d_past), hq, hkv, scale,
+        stream()))
+    torch.cuda.synchronize()
+    ref = _dense_ref(qkv, pre, layer, hq, hkv, specs, q_start, scale)
+    got = out.view(T, hq, KV.HD).float()
+    err = (got - ref).abs()
+    assert torch.allclose(got, ref, rtol=2e-2, atol=2e-2), (err.max(), err.argmax())
+
+
+def test_attn_prefill_dense_rescale_and_no_prefix():
+    """Large score magnitudes force the lazy running-max rescale of the TMEM accumulator
+    (O is rewritten through tcgen05.ld/st); prefix_kv may be NULL when nothing has a past."""
+    hq, hkv = 8, 2
+    specs = [(0, 700), (0, 260), (0, 31)]
+    qkv, pre, q_start, items, T = _dense_case(hq, hkv, specs, 0, 1, 0, seed=3, q_gain=6.0)
+    out = torch.zeros(T, hq * KV.HD, dtype=torch.bfloat16, device=DEV)
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
+    scale = 1.0 / math.sqrt(KV.HD)
+    d_items, d_qs = i32(items), i32(q_start)
+    d_ql, d_past = i32([q for _, q in specs]), i32([0] * len(specs))
+    L.check(L.lib().sb200_attn_prefill_dense(
+        L.ptr(qkv), qkv.shape[0], L.ptr(out), None, 0, 1, 0, L.ptr(d_items), len(items) // 2,
+        L.ptr(d_qs), L.ptr(d_ql), L.ptr(d_past), hq, hkv, scale, stream()))
+    torch.cuda.synchronize()
+    ref = _dense_ref(qkv, pre, 0, hq, hkv, specs, q_start, scale)
+    got = out.view(T, hq, KV.HD).float()
+    assert torch.allclose(got, ref, rtol=3e-2, atol=3e-2), (got - ref).abs().max()
+
+
+def test_attn_prefill_dense_is_batch_invariant():
+    """A sequence's output bits do not depend on which other sequences share the launch."""
+    hq, hkv = 32, 8
+    specs = [(46, 111), (46, 64), (46, 150), (0, 90)]
+    qkv, pre, q_start, items, T = _dense_case(hq, hkv, specs, 46, 1, 0, seed=9)
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
+    scale = 1.0 / math.sqrt(KV.HD)
+
+    def run(sel):
+        qt = L.lib().sb200_attn_prefill_q_tile(hq, hkv)
+        its = [x for i in sel for t0 in range(0, specs[i][1], qt) for x in (sel.index(i), t0)]
+        out = torch.zeros(T, hq * KV.HD, dtype=torch.bfloat16, device=DEV)
+        d_items, d_qs = i32(its), i32([q_start[i] for i in sel])
+        d_ql, d_past = i32([specs[i][1] for i in sel]), i32([specs[i][0] for i in sel])
+        L.check(L.lib().sb200_attn_prefill_dense(
+            L.ptr(qkv), qkv.shape[0], L.ptr(out), L.ptr(pre), 46, 1, 0, L.ptr(d_items),
+            len(its) // 2, L.ptr(d_qs), L.ptr(d_ql), L.ptr(d_past), hq, hkv, scale, stream()))
+        torch.cuda.synchronize()
+        return out
+    full = run([0, 1, 2, 3])
+    for i in range(4):
+        alone = run([i])
+        lo, hi = q_start[i], q_start[i] + specs[i][1]
+        assert torch.equal(alone[lo:hi], full[lo:hi])
+
+
 # --------------------------------------------------------------------------- FSM mask
 def test_fsm_build_mask_matches_python_walk():
     torch.manual_seed(0)

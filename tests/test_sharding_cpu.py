@@ -119,3 +119,132 @@ def test_infer_sharded_preserves_row_order_world2(n_rows):
         assert p.exitcode == 0
     lo, hi = shard_bounds(n_rows, 2, 0)
     assert out == [f"row-{i}@{0 if i < hi else 1}" for i in range(n_rows)]
+
+
+# --------------------------------------------------------------------------- sharded frame path
+class _CpuEngine:
+    """Stand-in for LocalEngine on CPU tensors: the orchestration in infer_frame_sharded
+    (broadcast, assignment, row selection, gather, ordered merge) is what is under test; the
+    'model' upper-cases a row and appends the rank that processed it."""
+
+    class _Spec:
+        embedding_model = False
+        d_model = 4
+
+    def __init__(self, rank, embedding=False):
+        import torch as _t
+        self.device = _t.device("cpu")
+        self.rank = rank
+        self.spec = self._Spec()
+        self.spec.embedding_model = embedding
+        self.seen_row_ids = None
+
+    def rows_select(self, d_bytes, d_off, part_rows, part_bytes, d_idx, capacity):
+        import numpy as np
+        import torch as _t
+        b, off, idx = d_bytes.numpy(), d_off.numpy(), d_idx.numpy()
+        out, ooff = [], [0]
+        for j in idx:
+            part, local = divmod(int(j), part_rows)
+            o = off[part * (part_rows + 1) + local: part * (part_rows + 1) + local + 2]
+            seg = b[part * part_bytes + o[0]: part * part_bytes + o[1]]
+            out.append(seg)
+            ooff.append(ooff[-1] + len(seg))
+        flat = np.concatenate(out) if out else np.zeros(0, np.uint8)
+        buf = np.zeros(max(capacity, 1), np.uint8)
+        buf[:len(flat)] = flat
+        return _t.tensor(ooff, dtype=_t.int64), _t.from_numpy(buf)
+
+    def run_blob_dev(self, d_text, d_off, n_rows, n_bytes, row_ids=None, suffix="", **kw):
+        import numpy as np
+        import torch as _t
+        self.seen_row_ids = None if row_ids is None else list(map(int, row_ids))
+        raw, off = d_text.numpy().tobytes(), d_off.numpy()
+        rows = [raw[off[i]:off[i + 1]].decode() for i in range(n_rows)]
+        if self.spec.embedding_model:
+            emb = np.array([[len(r), self.rank, i, 1.0] for i, r in enumerate(rows)], np.float32)
+            return dict(d_emb=_t.from_numpy(emb), stats={"rows_done": n_rows, "input_tokens": 1})
+        outs = [(r.upper() + f"@{self.rank}{suffix}").encode() for r in rows]
+        boff = np.zeros(n_rows + 1, np.int64)
+        boff[1:] = np.cumsum([len(o) for o in outs])
+        b = np.frombuffer(b"".join(outs), dtype=np.uint8).copy() if outs else np.zeros(1, np.uint8)
+        return dict(d_bytes=_t.from_numpy(b), d_boff=_t.from_numpy(boff),
+                    stats={"rows_done": n_rows, "input_tokens": int(off[-1]),
+                           "output_tokens": int(boff[-1])})
+
+
+_FRAME_ROWS = ["", "a", None, "héllo wörld", "x" * 40] + [f"row {i} " + "y" * ((i * 5) % 17)
+                                                           for i in range(31)]
+
+
+def _worker_frame(rank, world, port, balance, embedding, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from sutro_b200.sharding import infer_frame_sharded
+        eng = _CpuEngine(rank, embedding)
+        out = infer_frame_sharded(eng, _FRAME_ROWS if rank == 0 else None, src=0, balance=balance,
+                                  suffix="!")
+        if rank == 0:
+            q.put((out.get("outputs"), None if out.get("embeddings") is None
+                   else out["embeddings"].tolist(), out["stats"]["rows_done"],
+                   out["stats"]["n_gpus"]))
+        else:
+            assert out is None
+        assert eng.seen_row_ids is not None       # rows keep their job-wide ids on every rank
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("balance,embedding", [("bytes", False), ("rows", False), ("bytes", True)])
+def test_infer_frame_sharded_world2_is_positional(balance, embedding):
+    """The product's multi-GPU path on gloo: broadcast of the resident column, per-rank row
+    selection, per-rank run, padded gather, ordered merge — outputs[i] belongs to rows[i]."""
+    import numpy as np
+    from sutro_b200.sharding import shard_bounds as sb_, snake_assignment
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_frame, args=(r, 2, port, balance, embedding, q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    outputs, emb, rows_done, n_gpus = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    rows = ["" if r is None else r for r in _FRAME_ROWS]
+    lens = [len(r.encode()) for r in rows]
+    if balance == "bytes":
+        shards = snake_assignment(lens, 2)
+    else:
+        shards = [np.arange(*sb_(len(rows), 2, r)) for r in range(2)]
+    owner = {int(i): r for r, s in enumerate(shards) for i in s}
+    assert rows_done == len(rows) and n_gpus == 2
+    if embedding:
+        assert [e[0] for e in emb] == [float(len(r)) for r in rows]      # positional
+        assert [int(e[1]) for e in emb] == [owner[i] for i in range(len(rows))]
+    else:
+        assert outputs == [f"{rows[i].upper()}@{owner[i]}!" for i in range(len(rows))]
+    assert {owner[i] for i in range(len(rows))} == {0, 1}
+
+
+def test_infer_frame_sharded_single_process_matches():
+    from sutro_b200.sharding import infer_frame_sharded
+    out = infer_frame_sharded(_CpuEngine(0), _FRAME_ROWS)
+    rows = ["" if r is None else r for r in _FRAME_ROWS]
+    assert out["outputs"] == [r.upper() + "@0" for r in rows]
+    assert out["stats"]["n_gpus"] == 1 and out["t_total_s"] >= out["t_results_resident_s"]
+    assert infer_frame_sharded(_CpuEngine(0), [])["outputs"] == []
+
+
+def test_snake_assignment_equals_balanced_shards():
+    import random
+    from sutro_b200.sharding import snake_assignment
+    rng = random.Random(3)
+    for n in (0, 1, 5, 1000, 20001):
+        costs = [int(rng.lognormvariate(4.5, 0.6)) % 300 for _ in range(n)]   # many ties
+        for world in (1, 2, 3, 8):
+            a = balanced_shards(costs, world)
+            b = [s.tolist() for s in snake_assignment(costs, world)]
+            assert a == b
