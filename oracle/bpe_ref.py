@@ -65,3 +65,11 @@ class RefTokenizer:
         if max_prompt is not None:
             body = body[:max(0, max_prompt - len(pre) - len(suf))]
         return pre + body + suf
+
+    def decode(self, tokens) -> str:
+        """Token ids -> text: the tokens' byte strings concatenated, UTF-8 with errors replaced
+        (the detokenizer's contract, sutro_b200/engine.py blob_to_rows)."""
+        if not hasattr(self, "_blob"):
+            self._blob, self._off = self.v.byte_blob()
+        raw = b"".join(bytes(self._blob[self._off[t]:self._off[t + 1]]) for t in tokens)
+        return raw.decode("utf-8", errors="replace")

@@ -35,9 +35,12 @@ import torch.nn.functional as F
 BF = torch.bfloat16
 
 
+_EXACT = False   # RefModel.logits(..., exact=True): no intermediate rounding (see there)
+
+
 def _r(x: torch.Tensor) -> torch.Tensor:
     """round to bf16, keep computing in fp32"""
-    return x.to(BF).float()
+    return x if _EXACT else x.to(BF).float()
 
 
 def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
@@ -140,10 +143,18 @@ class RefModel:
 
     # -- public -----------------------------------------------------------
     @torch.no_grad()
-    def logits(self, ids: Sequence[int]) -> torch.Tensor:
-        """Teacher-forced fp32 logits for every position: [T, V]."""
-        h = self._forward(ids, 0, [None] * self.spec.n_layers)
-        return h @ self._lm_head().t()
+    def logits(self, ids: Sequence[int], exact: bool = False) -> torch.Tensor:
+        """Teacher-forced fp32 logits for every position: [T, V].  `exact=True` computes the
+        same network on the same bf16-valued weights WITHOUT the intermediate bf16 roundings
+        (fp32 throughout): the yardstick for how much of an engine-vs-oracle difference is the
+        rounding noise every bf16 pipeline carries (tests/test_zy_real_size_parity_gpu.py)."""
+        global _EXACT
+        old, _EXACT = _EXACT, bool(exact)
+        try:
+            h = self._forward(ids, 0, [None] * self.spec.n_layers)
+            return h @ self._lm_head().t()
+        finally:
+            _EXACT = old
 
     @torch.no_grad()
     def embed(self, ids: Sequence[int]) -> torch.Tensor:

@@ -31,6 +31,17 @@ def _client() -> Sutro:
     return _instance
 
 
+def configure(**kwargs) -> Sutro:
+    """(Re)create the process-wide client with constructor options — `devices`,
+    `engine_options` (max_slots, max_prefill_tokens, kv_pages, ...), `model_paths`, `verbose`,
+    `cache_dir`, `on_progress` (see `Sutro.__init__`).  The reference configures its singleton
+    through setters (set_api_key / set_base_url, sutro/sdk.py:58-95); a local engine's knobs
+    are construction-time."""
+    global _instance
+    _instance = Sutro(**kwargs)
+    return _instance
+
+
 def _bind(name):
     def call(*a, **kw):
         return getattr(_client(), name)(*a, **kw)
@@ -42,4 +53,4 @@ def _bind(name):
 for _n in _PUBLIC:
     globals()[_n] = _bind(_n)
 
-__all__ = _PUBLIC + ["Sutro", "JobStatus", "BaseSutroClient"]
+__all__ = _PUBLIC + ["Sutro", "JobStatus", "BaseSutroClient", "configure"]

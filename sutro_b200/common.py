@@ -107,6 +107,63 @@ def handle_data_helper(data, column: Union[str, List[str], None] = None):
     raise ValueError("Unsupported data type. Please provide a list, DataFrame, or file path.")
 
 
+def column_as_arrow(data, column: Union[str, List[str], None] = None):
+    """The same inputs as `handle_data_helper`, but as ONE Arrow string column (pyarrow Array /
+    ChunkedArray) whenever that can be had without creating a Python object per row: parquet
+    and csv files are read by pyarrow straight into Arrow buffers, DataFrame / Table columns
+    are converted by pyarrow's C++ loops.  The engine consumes the Arrow buffers directly
+    (bytes + offsets go to the GPU as they are; engine.rows_to_blob), which is what matters at
+    10^6 rows (BASELINE.json configs[3]).  Returns None when only the list path applies
+    (lists, multi-column concatenation, .txt files): callers then use handle_data_helper.
+    Argument errors are the reference's (sutro/common.py:117-147)."""
+    try:
+        import pyarrow as pa
+    except Exception:  # pragma: no cover
+        return None
+    if isinstance(data, list) or isinstance(column, list):
+        return None
+    arr = None
+    if isinstance(data, str) and not data.startswith("dataset-"):
+        ext = os.path.splitext(data)[1].lower()
+        if ext not in (".csv", ".parquet"):
+            return None
+        if column is None:
+            raise ValueError("Column name must be specified for CSV/Parquet input")
+        if ext == ".parquet":
+            import pyarrow.parquet as pq
+            arr = pq.read_table(data, columns=[column]).column(column)
+        else:
+            import pyarrow.csv as pacsv
+            arr = pacsv.read_csv(data, convert_options=pacsv.ConvertOptions(
+                include_columns=[column])).column(column)
+    elif _is_arrow_table(data):
+        if column is None:
+            raise ValueError("Column name must be specified for DataFrame input")
+        arr = data.column(column)
+    elif isinstance(data, pd.DataFrame):
+        if column is None:
+            raise ValueError("Column name must be specified for DataFrame input")
+        try:
+            arr = pa.Array.from_pandas(data[column])
+        except Exception:
+            return None
+    elif _is_polars_frame(data):
+        if column is None:
+            raise ValueError("Column name must be specified for DataFrame input")
+        try:
+            arr = data[column].to_arrow()
+        except Exception:
+            return None
+    if arr is None:
+        return None
+    if not (pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type)):
+        try:
+            arr = arr.cast(pa.large_string())        # numbers etc.: their text form
+        except Exception:
+            return None
+    return arr
+
+
 def normalize_output_schema(output_schema: Union[Dict[str, Any], Type[Any], None]):
     """BaseModel subclass -> .model_json_schema(); dict passthrough; else ValueError
     (reference: sutro/common.py:152-163)."""

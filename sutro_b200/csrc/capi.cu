@@ -2,6 +2,7 @@
 // integer status codes, never throws across the boundary.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/sutro_b200.h"
 #include "common.cuh"
@@ -52,8 +53,13 @@ int sb200_gemm_qkv_rope(const void* a, int a_rows, const void* w, void* qkv_out,
                         const void* cos_tab, const void* sin_tab, const int32_t* tok_slot,
                         const int32_t* tok_pos, const int32_t* page_table, int max_pages,
                         void* kv_layer, int hq, int hkv, float eps, void* stream) {
+  // SB200_QKV_DENSE=0: skip the dense K/V copy (A/B timing of the epilogue only)
+  static const int dense = [] {
+    const char* e = getenv("SB200_QKV_DENSE");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
   QkvEpiArgs ea{tok_pos, tok_slot, page_table, max_pages, kv_layer, cos_tab, sin_tab,
-                q_norm_w, k_norm_w, hq, hkv, eps};
+                q_norm_w, k_norm_w, hq, hkv, eps, dense};
   const int N = (hq + 2 * hkv) * kHeadDim;
   return gemm_bf16_tn(a, a_rows, w, qkv_out, nullptr, M, N, K, N, EPI_QKV_ROPE, block_n,
                       STREAM(stream), &ea);

@@ -313,7 +313,8 @@ struct Engine {
       if (fuse_qkv) {
         // K1+K5 fused: q/k-norm, RoPE and the paged K/V write happen in the GEMM epilogue
         QkvEpiArgs qa{tok_pos, tok_slot, page_table, max_pages, kv_layer(l), w.rope_cos,
-                      w.rope_sin, qn[l], kn[l], c.n_q_heads, c.n_kv_heads, c.rms_eps};
+                      w.rope_sin, qn[l], kn[l], c.n_q_heads, c.n_kv_heads, c.rms_eps,
+                      (prefill && prefill_tc) ? 1 : 0};
         gemm_flops += 2.0 * T * qkv_dim * c.d_model;
         SB_K(SB200_KC_GEMM, gemm_bf16_tn(h, t_max, wqkv[l], qkv, nullptr, T, qkv_dim, c.d_model,
                                          qkv_dim, EPI_QKV_ROPE, 0, stream, &qa));

@@ -226,7 +226,7 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
                                  pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
     st_v4(dst_lo + ((g ^ swz) << 3), olo);
     st_v4(dst_lo + (((g + 8) ^ swz) << 3), ohi);
-    if (!is_q) {
+    if (!is_q && ea.write_dense) {
       // dense copy next to q: the tcgen05 prefill attention reads the new tokens' K/V from the
       // qkv buffer through TMA (attn_prefill_tc.cu); decode reads the paged copy above
       __nv_bfloat16* dense = qkv_out + static_cast<size_t>(row) * ldd + head * kHeadDim;

@@ -46,6 +46,7 @@ struct QkvEpiArgs {
   const void* k_norm_w;
   int hq, hkv;
   float eps;
+  int write_dense;  // also leave post-norm/RoPE K and V in their qkv columns (dense prefill attention)
 };
 
 // K1 — D = A · W^T (+ fused epilogue); A:[a_rows>=M, K] bf16, W:[N,K] bf16.

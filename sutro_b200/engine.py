@@ -739,7 +739,8 @@ class MultiGpuEngine:
 
         from .sharding import balanced_shards, shard_bounds
         progress = kw.pop("progress", None)
-        rows = rows if isinstance(rows, list) else list(rows)
+        if not isinstance(rows, list):
+            rows = rows.to_pylist() if hasattr(rows, "to_pylist") else list(rows)
         n, g = len(rows), len(self.engines)
         if balance == "rows":
             shards = [list(range(*shard_bounds(n, g, r))) for r in range(g)]

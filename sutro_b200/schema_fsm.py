@@ -62,6 +62,33 @@ class ByteDFA:
         return bool(self.accept[s])
 
 
+    def longest_path(self) -> Optional[int]:
+        """Length in bytes of the longest string the automaton accepts, or None when it has a
+        cycle (an unbounded language).  Every token is at least one byte, so this bounds the
+        number of tokens a constrained row can need: the SDK sizes max_new_tokens from it."""
+        n = self.n_states
+        succ = [np.unique(self.trans[s][self.trans[s] >= 0]) for s in range(n)]
+        depth = [-1] * n          # longest path to a dead end, from s
+        state = [0] * n           # 0 new, 1 on stack, 2 done
+        stack = [(self.start, 0)]
+        while stack:
+            s, i = stack.pop()
+            if i == 0:
+                if state[s] == 2:
+                    continue
+                state[s] = 1
+            if i < len(succ[s]):
+                stack.append((s, i + 1))
+                t = int(succ[s][i])
+                if state[t] == 1:
+                    return None
+                if state[t] == 0:
+                    stack.append((t, 0))
+            else:
+                depth[s] = max([1 + depth[int(t)] for t in succ[s]], default=0)
+                state[s] = 2
+        return depth[self.start]
+
     # ---- forced runs (jump-forward decoding) --------------------------------------
     def forced_run(self, state: int):
         """Follow `state` while exactly one byte keeps the automaton alive and the state is
@@ -837,7 +864,17 @@ class _Compiler:
                 raise SchemaError(f"unsupported keyword {bad!r}")
         t = sch.get("type")
         if isinstance(t, list):
-            return b.alt(*[self.node({**sch, "type": x}) for x in t])
+            # {"type": ["string", "null"], "maxLength": 5}: every member type takes the keywords
+            # that apply to it (JSON Schema: a keyword for another type is vacuous)
+            typed = set().union(*self._KEYWORDS.values())
+            alts = []
+            for x in t:
+                if x not in self._KEYWORDS:
+                    raise SchemaError(f"unsupported type {x!r}")
+                keep = {k: v for k, v in sch.items()
+                        if k not in typed or k in self._KEYWORDS[x]}
+                alts.append(self.node({**keep, "type": x}))
+            return alts[0] if len(alts) == 1 else b.alt(*alts)
         if t is None:
             for name, keys in self._KEYWORDS.items():
                 if keys & set(sch):

@@ -30,8 +30,8 @@ from typing import Any, Dict, List, Optional, Type, Union
 import numpy as np
 import pandas as pd
 
-from .common import (ModelOptions, handle_data_helper, is_frame, normalize_output_schema, pl,
-                     to_colored_text)
+from .common import (ModelOptions, column_as_arrow, handle_data_helper, is_frame,
+                     normalize_output_schema, pl, to_colored_text)
 from .interfaces import BaseSutroClient, JobStatus
 from .templates import Templates
 
@@ -155,6 +155,47 @@ class Sutro(Templates, BaseSutroClient):
                                                              **self.engine_options)
         return self._engines[model]
 
+    @staticmethod
+    def _default_max_new_tokens(eng, json_schema) -> int:
+        """Output budget when sampling_params names none.  Schema jobs: the longest string the
+        schema's automaton accepts (every token is at least one byte), so a constrained row
+        can always close its object — a row cut mid-object would not be JSON.  Free text: 512."""
+        spec = getattr(eng, "spec", None)
+        cap = max(16, getattr(spec, "max_position", 4096) // 2)
+        if json_schema is not None and hasattr(eng, "compile_schema"):
+            longest = eng.compile_schema(json_schema).longest_path()
+            if longest is not None:
+                return int(min(max(longest, 8), cap))
+        return int(min(512, cap))
+
+    def _dispatch(self, eng, input_data, kw):
+        """The reference's one process boundary (`POST batch-inference`, sutro/sdk.py:223) as a
+        local call.  One GPU: `sb200_infer_text`, one C call with host buffers.  One process per
+        GPU under torchrun: the row-sharded path (sharding.infer_frame_sharded; rank 0 holds the
+        frame and receives the ordered results).  Several devices in this process:
+        MultiGpuEngine."""
+        import types
+        try:
+            import torch.distributed as dist
+            sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except Exception:
+            sharded = False
+        if sharded and hasattr(eng, "run_blob_dev"):
+            from .sharding import infer_frame_sharded
+            kw = dict(kw)
+            progress = kw.pop("progress", None)
+            out = infer_frame_sharded(eng, input_data if dist.get_rank() == 0 else None, src=0,
+                                      progress=progress, **kw)
+            if out is None:
+                return None
+            return types.SimpleNamespace(outputs=out.get("outputs"), embeddings=out.get("embeddings"),
+                                         stats=out["stats"], cum_logprobs=None)
+        if hasattr(eng, "infer_one_call"):
+            return eng.infer_one_call(input_data, return_tokens=False, **kw)
+        if not isinstance(input_data, list):      # engines without the Arrow-aware entry points
+            input_data = input_data.to_pylist()
+        return eng.generate(input_data, **kw)
+
     def register_engine(self, model: str, engine) -> None:
         """Use a pre-built LocalEngine (tests, benchmarks, multi-GPU workers)."""
         self._engines[model] = engine
@@ -169,7 +210,11 @@ class Sutro(Templates, BaseSutroClient):
         if description is not None and len(description) > JOB_DESCRIPTION_CHAR_LIMIT:
             raise ValueError(
                 f"Job description cannot exceed {JOB_DESCRIPTION_CHAR_LIMIT} characters.")
-        input_data = handle_data_helper(data, column)
+        # files and frame columns travel as Arrow buffers (no Python object per row); lists,
+        # multi-column concatenations and .txt files take the reference's list path
+        input_data = column_as_arrow(data, column)
+        if input_data is None:
+            input_data = handle_data_helper(data, column)
         # sampling_params is an opaque dict in the reference (forwarded as is, sdk.py:203);
         # the local engine understands the usual keys and rejects the rest loudly.
         sp = dict(sampling_params or {})
@@ -185,7 +230,8 @@ class Sutro(Templates, BaseSutroClient):
         if temperature < 0 or not (0.0 < top_p <= 1.0) or top_k < 0:
             raise ValueError("sampling_params: temperature >= 0, 0 < top_p <= 1, top_k >= 0")
         seed = int(sp.get("seed", sp.get("random_seed", 0)) or 0)
-        max_new = int(sp.get("max_tokens", sp.get("max_new_tokens", 64)))
+        max_new = sp.get("max_tokens", sp.get("max_new_tokens"))
+        max_new = None if max_new is None else int(max_new)
 
         job = _Job("job-" + uuid.uuid4().hex[:24], model, len(input_data), name, description,
                    job_priority)
@@ -200,23 +246,31 @@ class Sutro(Templates, BaseSutroClient):
             if cost_estimate:
                 # dry run: count input tokens only (the reference asks the service for a
                 # dollar estimate; locally the marginal cost is zero)
-                toks = eng.tokenizer.encode([("" if x is None else str(x)) for x in input_data])
+                as_list = input_data if isinstance(input_data, list) else input_data.to_pylist()
+                toks = eng.tokenizer.encode([("" if x is None else str(x)) for x in as_list])
                 job.stats = {"input_tokens": sum(map(len, toks))}
                 job.cost_estimate = 0.0
                 job.status = JobStatus.SUCCEEDED
                 self._say(f"✔ Cost estimates retrieved for job {job.job_id}: $0.0 "
                           f"({job.stats['input_tokens']} input tokens)", "success")
                 return job.job_id
+            if max_new is None:
+                max_new = self._default_max_new_tokens(eng, json_schema)
             t0 = time.perf_counter()
             stream = None
             if self.on_progress is not None or (stay_attached and self.verbose):
                 stream = _ProgressStream(job, self.on_progress,
                                          bar=bool(stay_attached and self.verbose))
-            res = eng.generate(input_data, system_prompt=system_prompt, json_schema=json_schema,
-                               max_new_tokens=max_new, ignore_eos=bool(sp.get("ignore_eos", False)),
-                               truncate_rows=truncate_rows, temperature=temperature, top_k=top_k,
-                               top_p=top_p, seed=seed, seed_per_row=bool(random_seed_per_input),
-                               return_logprobs=True, progress=stream)
+            kw = dict(system_prompt=system_prompt, json_schema=json_schema,
+                      max_new_tokens=max_new, ignore_eos=bool(sp.get("ignore_eos", False)),
+                      truncate_rows=truncate_rows, temperature=temperature, top_k=top_k,
+                      top_p=top_p, seed=seed, seed_per_row=bool(random_seed_per_input),
+                      return_logprobs=True, progress=stream)
+            res = self._dispatch(eng, input_data, kw)
+            if res is None:          # a non-source rank of a row-sharded job: nothing to report
+                job.status = JobStatus.SUCCEEDED
+                job.outputs = []
+                return job.job_id
             dt = time.perf_counter() - t0
             if stream is not None:
                 stream.close()
@@ -293,6 +347,7 @@ class Sutro(Templates, BaseSutroClient):
         truncate_rows: bool = True,
     ):
         """Run inference over `data` on the local B200 engine; returns the job id."""
+        model = self._resolve_model(model)
         if stay_attached is None:
             stay_attached = job_priority == 0
         json_schema = None
@@ -302,6 +357,26 @@ class Sutro(Templates, BaseSutroClient):
                                              json_schema, sampling_params, system_prompt, dry_run,
                                              stay_attached, random_seed_per_input, truncate_rows,
                                              name, description)
+
+    # the reference's default model is served by its hosted service only; scripts that rely on
+    # the default keep working here on the local flagship
+    LOCAL_DEFAULT_MODEL = "qwen-3-4b"
+
+    def _resolve_model(self, model: str) -> str:
+        from . import modelspec as MS
+        if model in self._engines or model in self.model_paths:
+            return model
+        try:
+            MS.get_spec(model)
+            return model
+        except ValueError:
+            if model == "gemma-3-12b-it":
+                self._say(f"Model {model!r} (the hosted service's default) has no local engine; "
+                          f"running {self.LOCAL_DEFAULT_MODEL!r} instead")
+                return self.LOCAL_DEFAULT_MODEL
+            raise ValueError(f"Unknown model {model!r}: local engines exist for "
+                             f"{sorted(MS.SPECS)} and for directories named in model_paths "
+                             f"({sorted(self.model_paths)})")
 
     def infer_per_model(self, data, models: List[ModelOptions], names: List[str] = None,
                         descriptions: List[str] = None, column=None,
@@ -379,7 +454,7 @@ class Sutro(Templates, BaseSutroClient):
         path = os.path.join(self.cache_dir, f"{job_id}.snappy.parquet")
         cols: Dict[str, Any] = {}
         if include_inputs:
-            cols["inputs"] = j.inputs
+            cols["inputs"] = j.inputs if isinstance(j.inputs, list) else j.inputs.to_pylist()
         cols[output_column] = j.outputs
         if include_cumulative_logprobs:
             cols["cumulative_logprobs"] = [float(x) for x in j.cum_logprobs]
@@ -396,7 +471,7 @@ class Sutro(Templates, BaseSutroClient):
                     vec = pa.FixedSizeListArray.from_arrays(pa.array(emb.reshape(-1)), emb.shape[1])
                     names, arrays = [output_column], [vec]
                     if include_inputs:
-                        names, arrays = ["inputs"] + names, [pa.array(j.inputs)] + arrays
+                        names, arrays = ["inputs"] + names, [pa.array(cols["inputs"])] + arrays
                     pq.write_table(pa.table(arrays, names=names), path, compression="snappy")
                 else:
                     df.to_parquet(path, compression="snappy")
@@ -406,13 +481,20 @@ class Sutro(Templates, BaseSutroClient):
             try:
                 first = json.loads(df[output_column].iloc[0])
                 if isinstance(first, dict):
-                    decoded = [json.loads(s) for s in df[output_column]]
+                    def _loads(x):   # a row that is not JSON (cut by max_tokens) unpacks to None
+                        try:
+                            return json.loads(x)
+                        except (TypeError, ValueError):
+                            return None
+                    decoded = [_loads(x) for x in df[output_column]]
                     for key in first.keys():
                         df[key] = [d.get(key) if isinstance(d, dict) else None for d in decoded]
                     if sorted(first.keys()) == ["content", "reasoning_content"] and \
                             isinstance(first["content"], dict):
                         for key in first["content"].keys():
-                            df[key] = [d["content"].get(key) for d in decoded]
+                            df[key] = [d["content"].get(key)
+                                       if isinstance(d, dict) and isinstance(d.get("content"), dict)
+                                       else None for d in decoded]
                         df = df.drop(columns=["content"])
                     if output_column not in first:   # a key may reuse the column's name (rank)
                         df = df.drop(columns=[output_column])

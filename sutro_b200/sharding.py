@@ -155,6 +155,10 @@ def infer_frame_sharded(engine, rows=None, src: int = 0, balance: str = "bytes",
         h2d = 0
     sync()
     t_res = time.perf_counter()
+    ev = None
+    if is_cuda:    # device time of "column resident -> ordered results resident" on this rank
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     if multi:
         dist.broadcast(hdr, src=src)
         n_rows, n_bytes = (int(x) for x in hdr.cpu())
@@ -189,6 +193,8 @@ def infer_frame_sharded(engine, rows=None, src: int = 0, balance: str = "bytes",
     # ---- gather on src, ordered merge ------------------------------------------------------
     out: dict = {}
     if world == 1:
+        if ev:
+            ev[1].record()
         sync()
         t_out = time.perf_counter()
         if emb_mode:
@@ -233,6 +239,8 @@ def infer_frame_sharded(engine, rows=None, src: int = 0, balance: str = "bytes",
         if rank != src:
             return None
         if emb_mode:
+            if ev:
+                ev[1].record()
             sync()
             t_out = time.perf_counter()
             emb = np.empty((n_rows, engine.spec.d_model), dtype=np.float32)
@@ -248,6 +256,8 @@ def infer_frame_sharded(engine, rows=None, src: int = 0, balance: str = "bytes",
             d_sel = torch.from_numpy(sel).to(dev)
             d_ooff, d_obytes = engine.rows_select(bytes_all, off_all, max_m, max_b, d_sel,
                                                   int(bytes_all.numel()))
+            if ev:
+                ev[1].record()
             sync()
             t_out = time.perf_counter()
             boff = d_ooff.cpu().numpy()
@@ -256,7 +266,8 @@ def infer_frame_sharded(engine, rows=None, src: int = 0, balance: str = "bytes",
             d2h = b.nbytes + boff.nbytes
     t_end = time.perf_counter()
     agg = {"n_gpus": world, "n_rows": n_rows, "h2d_bytes": h2d, "d2h_bytes": int(d2h),
-           "per_gpu": stats}
+           "per_gpu": stats,
+           "t_device_ms": ev[0].elapsed_time(ev[1]) if ev else 1e3 * (t_out - t_res)}
     for k in ("input_tokens", "output_tokens", "decode_tokens", "prefill_tokens", "rows_done",
               "rows_truncated", "prefill_steps", "decode_steps"):
         agg[k] = sum(int(s.get(k, 0)) for s in stats if s)

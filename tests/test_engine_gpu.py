@@ -183,8 +183,13 @@ def test_prefix_sharing_and_batch_geometry_do_not_change_results():
                       return_tokens=True).out_tokens
     same_ab = sum(x == y for x, y in zip(a, b))
     same_ac = sum(x == y for x, y in zip(a, c))
-    # identical math per row; only fp32 summation order inside GEMM tiles may differ
-    assert same_ab >= 38 and same_ac >= 36, (same_ab, same_ac)
+    record_parity("batch_geometry(share_prefix off / 4 slots)", len(rows), same_ab, same_ac, 0)
+    # a different batch geometry (slots, prefill packing, admission order) must not change a
+    # single token: no kernel choice depends on the batch.  Without prefix sharing the prefix
+    # is recomputed inside each row's own KV blocks — another summation order, so near-tie
+    # decisions may move.
+    assert same_ac == 40, same_ac
+    assert same_ab >= 36, same_ab
 
 
 @pytest.mark.parametrize("jump", [True, False])

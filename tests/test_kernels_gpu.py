@@ -69,6 +69,69 @@ def test_gemm_exact_integers():
     assert torch.equal(d, ref)
 
 
+@pytest.mark.parametrize("M,N,K,epi", [
+    (32768, 19456, 2560, 3),     # gate/up shape of qwen-3-4b at a full prefill step (fp32 out)
+    (32768, 2560, 9728, 0),      # down projection
+    (32768, 6144, 2560, 0),      # QKV
+    (32768, 2560, 4096, 1),      # O projection + residual
+    (3584, 2560, 9728, 1),       # decode batch: down + residual
+    (3584, 19456, 2560, 0),      # decode batch: gate/up rows
+    (20000, 4096, 4096, 0),      # llama-3.1-8b width, M not a multiple of the tile
+])
+def test_gemm_exact_integers_at_the_benchmark_shapes(M, N, K, epi):
+    """The shapes that earn the roofline number (multi-group raster, many waves, K up to
+    9728), on small-integer operands: every partial sum is exact in fp32, so the kernel must
+    agree BIT FOR BIT with a plain fp32 matmul (+ the documented bf16 rounding points),
+    whatever tile shape, raster order or CTA pairing the launcher picked."""
+    torch.manual_seed(M + N + K)
+    a = bf(torch.randint(-2, 3, (M, K), device=DEV).float())
+    w = bf(torch.randint(-2, 3, (N, K), device=DEV).float())
+    acc = a.float() @ w.float().t()          # exact: |sum| <= 4*9728 < 2^24
+    if epi == 3:
+        assert torch.equal(_gemm(a, w, 3), acc)
+    elif epi == 0:
+        assert torch.equal(_gemm(a, w, 0), bf(acc))
+    else:
+        r = bf(torch.randint(-64, 65, (M, N), device=DEV).float())
+        out = r.clone()
+        _gemm(a, w, 1, resid=out, out=out)
+        assert torch.equal(out, bf(bf(acc).float() + r.float()))
+    del acc
+
+
+def test_gemm_swiglu_at_the_benchmark_shape():
+    M, F, K = 16384, 9728, 2560
+    torch.manual_seed(11)
+    a = bf(torch.randn(M, K, device=DEV))
+    w = bf(torch.randn(2 * F, K, device=DEV) / math.sqrt(K))
+    d = _gemm(a, w, 2)
+    acc = a.float() @ w.float().t()
+    g, u = bf(acc[:, 0::2]).float(), bf(acc[:, 1::2]).float()
+    ref = bf(bf(torch.nn.functional.silu(g)).float() * u)
+    assert d.shape == (M, F)
+    assert torch.allclose(d.float(), ref.float(), rtol=3e-2, atol=2e-2)
+    assert (d != ref).float().mean().item() < 0.02       # rounding-boundary cases only
+
+
+def test_gemm_tile_configurations_are_bit_identical():
+    """Batch invariance of the GEMM: the launcher picks the tile shape from M (128x64 ...
+    256x256 CTA pair), so a row's result must not depend on that choice — every configuration
+    accumulates over K in the same order (k-blocks of 64, four K=16 UMMA steps each)."""
+    torch.manual_seed(21)
+    M, N, K = 300, 1536, 2560
+    a = bf(torch.randn(M, K, device=DEV))
+    w = bf(torch.randn(N, K, device=DEV) / math.sqrt(K))
+    outs = {bn: _gemm(a, w, 3, block_n=bn) for bn in (64, 128, 256, 512)}
+    for bn in (128, 256, 512):
+        diff = (outs[bn] != outs[64]).float().mean().item()
+        assert diff == 0.0, (bn, diff, (outs[bn] - outs[64]).abs().max().item())
+    # and the rows of a small batch equal the same rows inside a big one
+    big = bf(torch.randn(5000, K, device=DEV))
+    big[1000:1000 + M] = a
+    full = _gemm(big, w, 3)
+    assert torch.equal(full[1000:1000 + M], outs[64])
+
+
 def test_gemm_a_rows_larger_than_m():
     M, N, K = 200, 512, 256
     torch.manual_seed(2)

@@ -274,3 +274,25 @@ def test_recursive_models_are_unrolled_to_a_fixed_depth():
     with pytest.raises(SchemaError):                 # a cycle with no way to stop
         compile_schema({"$defs": {"A": {"type": "object", "properties": {"a": {"$ref": "#/$defs/A"}},
                                         "required": ["a"]}}, "$ref": "#/$defs/A"}, LIM)
+
+
+def test_type_list_with_keywords_of_one_member():
+    """{"type": ["string", "null"], "maxLength": 5}: maxLength applies to the string branch
+    only (it is vacuous for null), the schema compiles, both branches are accepted."""
+    from sutro_b200.schema_fsm import compile_schema
+    d = compile_schema({"type": ["string", "null"], "maxLength": 5})
+    assert d.matches(b"null") and d.matches(b'"abcde"') and not d.matches(b'"abcdef"')
+    d = compile_schema({"type": ["integer", "string"], "minimum": 3, "maximum": 9, "maxLength": 1})
+    assert d.matches(b"7") and not d.matches(b"2") and d.matches(b'"x"') and not d.matches(b'"xy"')
+
+
+def test_longest_path_bounds_every_accepted_string():
+    from sutro_b200.schema_fsm import FsmLimits, compile_schema
+    d = compile_schema({"type": "object", "properties": {"sentiment": {"type": "string", "enum": [
+        "positive", "neutral", "negative"]}}, "required": ["sentiment"]})
+    assert d.longest_path() == len('{"sentiment":"positive"}')
+    d = compile_schema({"type": "array", "items": {"type": "integer", "minimum": 0, "maximum": 99},
+                        "maxItems": 3})
+    assert d.longest_path() == len("[99,99,99]")
+    d = compile_schema({"type": "string"}, FsmLimits(max_string_chars=4))
+    assert d.longest_path() == 2 + 4 * 6        # four \\uXXXX escapes between the quotes

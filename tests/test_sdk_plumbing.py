@@ -414,3 +414,91 @@ def test_start_up_calls_of_reference_scripts_are_accepted():
         c.upload_to_dataset("d", ["f.parquet"])
     for name in ("set_api_key", "set_base_url", "get_quotas", "attach", "rank", "elo", "infer"):
         assert callable(getattr(so, name))
+
+
+# --------------------------------------------------------------------------- round-2 fixes
+class _CutEngine(StubEngine):
+    """One row comes back cut mid-object (what max_tokens below the schema's need does)."""
+
+    def generate(self, rows, **kw):
+        r = super().generate(rows, **kw)
+        r.outputs[1] = '{"sentiment":"s'
+        return r
+
+
+def test_one_unparsable_row_does_not_disable_json_unpacking():
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+    c.register_engine("qwen-3-4b", _CutEngine())
+    job = c.infer(["a", "b", "c"], model="qwen-3-4b", output_schema=Sentiment, stay_attached=False)
+    df = c.get_job_results(job)
+    got = list(df["sentiment"])
+    assert got[0] == "s0" and got[2] == "s2" and pd.isna(got[1])     # pandas shows None as NaN
+
+
+def test_default_output_budget_comes_from_the_schema():
+    """No max_tokens in sampling_params: a schema job gets the longest string its automaton
+    accepts (so a constrained row can always finish), free text gets 512."""
+    from sutro_b200.schema_fsm import compile_schema
+
+    class Eng(StubEngine):
+        class spec:
+            max_position = 4096
+
+        def compile_schema(self, schema, limits=None):
+            return compile_schema(schema, limits)
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+    eng = Eng()
+    c.register_engine("qwen-3-4b", eng)
+    enum_schema = {"type": "object", "properties": {"sentiment": {"type": "string", "enum": [
+        "positive", "neutral", "negative"]}}, "required": ["sentiment"]}
+    c.infer(["x"], model="qwen-3-4b", output_schema=enum_schema, stay_attached=False)
+    assert eng.calls[-1][1]["max_new_tokens"] == len('{"sentiment":"positive"}')
+    c.infer(["x"], model="qwen-3-4b", stay_attached=False)
+    assert eng.calls[-1][1]["max_new_tokens"] == 512
+    c.infer(["x"], model="qwen-3-4b", sampling_params={"max_tokens": 7}, stay_attached=False)
+    assert eng.calls[-1][1]["max_new_tokens"] == 7
+
+
+def test_reference_default_model_maps_to_the_local_flagship():
+    c = client()
+    job = c.infer(["x"], stay_attached=False)            # model defaults to gemma-3-12b-it
+    assert c.fetch_job(job)["model"] == "qwen-3-4b"
+    with pytest.raises(ValueError, match="Unknown model"):
+        c.infer(["x"], model="no-such-model")
+    assert not any(j["model"] == "no-such-model" for j in c.list_jobs())   # no FAILED record
+
+
+def test_files_and_frame_columns_travel_as_arrow(tmp_path):
+    """csv / parquet paths and DataFrame columns reach an Arrow-aware engine as ONE Arrow
+    column (no Python object per row); lists and multi-column concatenations keep the
+    reference's list path (sutro/common.py:111-149)."""
+    import pyarrow as pa
+
+    class ArrowEngine(StubEngine):
+        def infer_one_call(self, rows, **kw):
+            self.calls.append((rows, kw))
+            n = len(rows)
+            return GenerationResult([f"o{i}" for i in range(n)], None, None,
+                                    {"input_tokens": 1, "output_tokens": 1})
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+    eng = ArrowEngine(as_json=False)
+    c.register_engine("qwen-3-4b", eng)
+    df = pd.DataFrame({"t": ["a", None, "c"], "n": [1, 2, 3]})
+    df.to_parquet(tmp_path / "f.parquet")
+    df.to_csv(tmp_path / "f.csv", index=False)
+    for data in (df, str(tmp_path / "f.parquet"), str(tmp_path / "f.csv")):
+        job = c.infer(data, model="qwen-3-4b", column="t", stay_attached=False)
+        rows = eng.calls[-1][0]
+        assert isinstance(rows, (pa.Array, pa.ChunkedArray)) and len(rows) == 3
+        data_b, off = rows_to_blob(rows)
+        assert blob_to_rows(data_b, off)[0] == "a" and blob_to_rows(data_b, off)[2] == "c"
+        res = c.get_job_results(job, include_inputs=True)
+        assert list(res["inputs"])[0] == "a" and len(res) == 3
+    c.infer(df, model="qwen-3-4b", column="n", stay_attached=False)       # numbers: their text form
+    assert blob_to_rows(*rows_to_blob(eng.calls[-1][0])) == ["1", "2", "3"]
+    c.infer(["x", "y"], model="qwen-3-4b", stay_attached=False)
+    assert eng.calls[-1][0] == ["x", "y"]
+    c.infer(df, model="qwen-3-4b", column=["t", ": ", "n"], stay_attached=False)
+    assert eng.calls[-1][0] == ["a: 1", ": 2", "c: 3"]
+    with pytest.raises(ValueError, match="Column name must be specified"):
+        c.infer(str(tmp_path / "f.parquet"), model="qwen-3-4b")
