@@ -279,6 +279,37 @@ int sb200_infer_text(void* engine, void* tokenizer, const uint8_t* rows_bytes,
                      sb200_job_stats* stats);
 void sb200_result_free(sb200_result* result);
 
+/* ------------------------------------------------------------------------
+ * output_schema -> automaton, natively.  The reference sends the JSON schema itself to its
+ * service (payload["json_schema"], sutro/sdk.py:199; built by normalize_output_schema,
+ * sutro/common.py:152-163).  sb200_schema_compile takes that JSON text and returns the byte
+ * DFA the engine consumes (sb200_job.fsm_trans / fsm_accept / fsm_final); caps for unbounded
+ * strings / arrays / integers come from sb200_fsm_limits (NULL = defaults).  Supported:
+ * objects with declared properties, strings (min/maxLength), integer / number bounds,
+ * booleans, null, arrays (items, min/maxItems), enum, const, anyOf / oneOf, compatible
+ * allOf, $ref into $defs, type lists.  A keyword outside that set that would constrain the
+ * output is an error (-2 = argument error), never ignored.  The tables stay owned by the
+ * schema handle until sb200_schema_destroy.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int max_string_chars; /* cap when a string has no maxLength (default 64)      */
+  int max_array_items;  /* cap when an array has no maxItems (8)                 */
+  int max_int_digits;   /* digits of an unbounded integer (9)                    */
+  int max_frac_digits;  /* fraction digits of a number (4)                       */
+  int small_int_range;  /* integer ranges up to this size are enumerated (2048)  */
+  int max_recursion;    /* how often a recursive $ref may be re-entered (2)      */
+} sb200_fsm_limits;
+
+void sb200_fsm_limits_default(sb200_fsm_limits* limits);
+int sb200_schema_compile(const char* json_utf8, int64_t len, const sb200_fsm_limits* limits,
+                         void** out_schema);
+void sb200_schema_destroy(void* schema);
+int sb200_schema_tables(void* schema, const int32_t** trans, const uint8_t** accept,
+                        const uint8_t** final_states, int* n_states, int* start);
+/* bytes of the longest accepted string (an upper bound on the tokens a constrained row can
+ * need), -1 when the language is unbounded */
+int64_t sb200_schema_longest_path(void* schema);
+
 /* Device-side Arrow helpers used by the Python host instead of tensor-library ops.
  * compact_rows: out_tokens[n_rows, stride] with len[i] valid tokens per row -> off[n_rows+1]
  * and the flat token array (capacity n_rows*stride).

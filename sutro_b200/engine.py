@@ -111,6 +111,52 @@ L.register("sb200_rows_select", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c
                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p])
 
 
+class FsmLimitsC(C.Structure):       # sb200_fsm_limits
+    _fields_ = [(n, C.c_int) for n in ("max_string_chars", "max_array_items", "max_int_digits",
+                                       "max_frac_digits", "small_int_range", "max_recursion")]
+
+
+L.register("sb200_fsm_limits_default", None, [C.POINTER(FsmLimitsC)])
+L.register("sb200_schema_compile", C.c_int, [C.c_char_p, C.c_int64, C.POINTER(FsmLimitsC),
+                                             C.POINTER(C.c_void_p)])
+L.register("sb200_schema_destroy", None, [C.c_void_p])
+L.register("sb200_schema_tables", C.c_int, [C.c_void_p, C.POINTER(c_i32p), C.POINTER(c_u8p),
+                                            C.POINTER(c_u8p), C.POINTER(C.c_int),
+                                            C.POINTER(C.c_int)])
+L.register("sb200_schema_longest_path", C.c_int64, [C.c_void_p])
+
+
+def native_compile_schema(schema: Dict[str, Any], limits: Optional[FsmLimits] = None) -> ByteDFA:
+    """JSON schema -> ByteDFA through the C-ABI compiler (csrc/schema_compile.cu): what a
+    non-Python host calls.  Raises SchemaError (a ValueError) for argument errors, exactly
+    like schema_fsm.compile_schema; the Python compiler covers a larger keyword set."""
+    import json
+
+    from .schema_fsm import SchemaError
+    text = json.dumps(schema, ensure_ascii=False).encode("utf-8")
+    lim = None
+    if limits is not None:
+        lim = FsmLimitsC(limits.max_string_chars, limits.max_array_items, limits.max_int_digits,
+                         limits.max_frac_digits, limits.small_int_range, limits.max_recursion)
+    h = C.c_void_p()
+    rc = L.lib().sb200_schema_compile(text, len(text), None if lim is None else C.byref(lim),
+                                      C.byref(h))
+    if rc != 0:
+        msg = L.lib().sb200_last_error().decode("utf-8", "replace")
+        raise SchemaError(msg) if rc == -2 else L.Sb200Error(msg)
+    try:
+        tr, ac, fi = c_i32p(), c_u8p(), c_u8p()
+        n, start = C.c_int(), C.c_int()
+        L.check(L.lib().sb200_schema_tables(h, C.byref(tr), C.byref(ac), C.byref(fi), C.byref(n),
+                                            C.byref(start)))
+        ns = n.value
+        return ByteDFA(np.ctypeslib.as_array(tr, shape=(ns, 256)).copy(),
+                       np.ctypeslib.as_array(ac, shape=(ns,)).copy(),
+                       np.ctypeslib.as_array(fi, shape=(ns,)).copy(), int(start.value))
+    finally:
+        L.lib().sb200_schema_destroy(h)
+
+
 def _np_ptr(a: np.ndarray, typ):
     return a.ctypes.data_as(typ)
 
