@@ -310,6 +310,35 @@ int sb200_schema_tables(void* schema, const int32_t** trans, const uint8_t** acc
  * need), -1 when the language is unbounded */
 int64_t sb200_schema_longest_path(void* schema);
 
+/* ------------------------------------------------------------------------
+ * A model on disk and the strings-only call: the whole request of the reference's
+ * `POST batch-inference` payload — model, inputs, system_prompt, json_schema, sampling_params
+ * (sutro/sdk.py:196-208) — served without any Python on the host side.
+ *
+ * sb200_model_open reads a bundle directory written by `python -m sutro_b200.bundle`
+ * (manifest.json + data.bin: architecture, bf16 weights in the engine's layout, RoPE tables,
+ * tokenizer tables, special-token ids, template family), uploads the weights and creates the
+ * engine and the GPU tokenizer.  max_slots / max_prefill_tokens / kv_pages <= 0 pick defaults
+ * (512 / 8192 / 80 % of the free memory).
+ *
+ * sb200_model_infer renders the chat template around `system_prompt_utf8` (NULL/"" = none),
+ * compiles `json_schema_utf8` (NULL = unconstrained) with sb200_schema_compile, derives the
+ * jump-forward plan from the automaton, picks max_new_tokens when <= 0 (the longest string the
+ * schema admits, else 512; capped at half the context window) and runs sb200_infer_text on the
+ * rows.  `sampling` may be NULL (greedy); only its temperature / top_k / top_p / seed /
+ * seed_per_row / ignore_eos / truncate_rows / progress fields are read.
+ * ---------------------------------------------------------------------- */
+int sb200_model_open(const char* bundle_dir, int device, int max_slots, int max_prefill_tokens,
+                     int64_t kv_pages, void** out_model);
+void sb200_model_close(void* model);
+void* sb200_model_engine(void* model);
+void* sb200_model_tokenizer(void* model);
+int sb200_model_infer(void* model, const char* system_prompt_utf8, const char* json_schema_utf8,
+                      int64_t schema_len, const sb200_fsm_limits* limits, int max_new_tokens,
+                      const sb200_job* sampling, const uint8_t* rows_bytes,
+                      const int64_t* rows_offsets, int64_t n_rows, int want_logprobs,
+                      sb200_result** out, sb200_job_stats* stats);
+
 /* Device-side Arrow helpers used by the Python host instead of tensor-library ops.
  * compact_rows: out_tokens[n_rows, stride] with len[i] valid tokens per row -> off[n_rows+1]
  * and the flat token array (capacity n_rows*stride).

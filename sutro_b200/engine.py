@@ -124,6 +124,14 @@ L.register("sb200_schema_tables", C.c_int, [C.c_void_p, C.POINTER(c_i32p), C.POI
                                             C.POINTER(c_u8p), C.POINTER(C.c_int),
                                             C.POINTER(C.c_int)])
 L.register("sb200_schema_longest_path", C.c_int64, [C.c_void_p])
+L.register("sb200_model_open", C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                         C.POINTER(C.c_void_p)])
+L.register("sb200_model_close", None, [C.c_void_p])
+L.register("sb200_model_engine", C.c_void_p, [C.c_void_p])
+L.register("sb200_model_tokenizer", C.c_void_p, [C.c_void_p])
+L.register("sb200_model_infer", C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int64,
+                                          C.POINTER(FsmLimitsC), C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p])
 
 
 def native_compile_schema(schema: Dict[str, Any], limits: Optional[FsmLimits] = None) -> ByteDFA:

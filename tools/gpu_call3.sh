@@ -2,9 +2,9 @@
 set -u
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_real_size.jsonl
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py tests/test_zy_real_size_parity_gpu.py -q --timeout 900 -p no:cacheprovider \
-   -k "tile_configurations or row_order or real_size" 2>&1 | tail -60 > gpurun_out/c3_pytest.txt
-tail -45 gpurun_out/c3_pytest.txt
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py tests/test_zy_real_size_parity_gpu.py tests/test_c_host_gpu.py -q --timeout 900 -p no:cacheprovider \
+   -k "tile_configurations or row_order or real_size or c_program" 2>&1 | tail -80 > gpurun_out/c3_pytest.txt
+tail -70 gpurun_out/c3_pytest.txt
 SB200_QKV_DENSE=1 timeout 120 python tools/qkv_epi_bench.py 2>&1 | tail -3
 SB200_QKV_DENSE=0 timeout 120 python tools/qkv_epi_bench.py 2>&1 | head -1
 timeout 200 python tools/gemm_bench.py 32768 2>&1 | grep -v "variant=51[46]" | tail -12
