@@ -275,6 +275,47 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
     const int sw = r & 7;
     uint32_t g = 0, n = 0;
     float m_used = 0.f, l_run = 0.f;
+    // The epilogue of an item is deferred until the first block of the NEXT item has been
+    // handed to the tensor core: the wait for the last P.V (O_FULL) then overlaps useful work
+    // instead of idling the softmax warps once per item (O is double-buffered).
+    bool ep_pending = false;
+    uint32_t ep_ob = 0, ep_par = 0;
+    float ep_inv = 0.f;
+    bool ep_row_ok = false;
+    __nv_bfloat16* ep_dst = nullptr;
+    auto flush_epilogue = [&]() {
+      if (!ep_pending) return;
+      ep_pending = false;
+      mbar_wait(bar(O_FULL + ep_ob), ep_par);
+      tc_fence_after();
+      const uint32_t o_addr = tmem_o + ep_ob * 128 + lane_sel;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {   // two 64-column halves: 64 live registers
+        uint32_t v[2][32];
+        tmem_ld_32x32(o_addr + half * 64, v[0]);
+        tmem_ld_32x32(o_addr + half * 64 + 32, v[1]);
+        tmem_ld_wait();
+        if (half == 1) {  // the accumulator has left TMEM: hand O[ob] back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(O_EMPTY + ep_ob));
+        }
+        if (ep_row_ok) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              o[i] = pack_bf16x2(__uint_as_float(v[c][2 * i]) * ep_inv,
+                                 __uint_as_float(v[c][2 * i + 1]) * ep_inv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              st_v4(ep_dst + half * 64 + c * 32 + 8 * i,
+                    make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+          }
+        }
+      }
+    };
     for (int item = blockIdx.x; item < n_items_total; item += gridDim.x, ++n) {
       const TcGeom ge = tc_geom<G>(item, hkv, items, seq_q_start, seq_q_len, seq_past);
       const int q_own = ge.qt0 + t_in;    // index of this row's token among the own tokens
@@ -290,16 +331,23 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
         mbar_wait(bar(S_FULL + sb), (g >> 1) & 1);
         tc_fence_after();
         const uint32_t s_addr = tmem_s + sb * 128 + lane_sel;
-        // ---- pass 1: row max of the valid scores ----
-        float mx = -INFINITY;
-        for (int c = 0; c < n_chunks; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_addr + c * 32, v);
-          tmem_ld_wait();
+        // ---- the whole score row into registers (one TMEM round trip), S[sb] released ----
+        uint32_t v[4][32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < vlim) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
+        for (int c = 0; c < 4; ++c)
+          if (c < n_chunks) tmem_ld_32x32(s_addr + c * 32, v[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < n_chunks) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < vlim) mx = fmaxf(mx, __uint_as_float(v[c][i]));
+          }
         mx *= scale_log2;  // scale > 0: max commutes with the scaling
         // ---- running max with lazy rescale ----
         float alpha = 1.f;
@@ -313,6 +361,26 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
           l_run *= alpha;
           need = true;
         }
+        // ---- P = exp2(s*scale - m) -> bf16 (registers) ----
+        float psum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < n_chunks) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {   // packed pairs overwrite the scores in place
+              const int c0 = c * 32 + 2 * i;
+              const float p0 = c0 < vlim
+                                   ? exp2f(fmaf(__uint_as_float(v[c][2 * i]), scale_log2, -m_used))
+                                   : 0.f;
+              const float p1 =
+                  c0 + 1 < vlim
+                      ? exp2f(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2, -m_used))
+                      : 0.f;
+              psum += p0 + p1;
+              v[c][i] = pack_bf16x2(p0, p1);
+            }
+          }
+        l_run += psum;
         // the previous block's PV must have retired before O is rescaled or P is overwritten
         mbar_wait(bar(P_EMPTY), (g & 1) ^ 1);
         if (__any_sync(0xffffffffu, need)) {
@@ -320,85 +388,46 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
           const uint32_t o_addr = tmem_o + ob * 128 + lane_sel;
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(o_addr + c * 32, v);
+            uint32_t o[32];
+            tmem_ld_32x32(o_addr + c * 32, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st_32x32(o_addr + c * 32, v);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(o_addr + c * 32, o);
           }
           tmem_st_wait();
+          tc_fence_before();
         }
-        // ---- pass 2: P = exp2(s*scale - m) -> bf16 -> shared memory (K-major, SW128) ----
-        float psum = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_addr + c * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
+        // ---- P -> shared memory (K-major, SW128): 32 columns = four 16-byte chunks ----
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c0 = c * 32 + 2 * i;
-            const float p0 =
-                c0 < vlim ? exp2f(fmaf(__uint_as_float(v[2 * i]), scale_log2, -m_used)) : 0.f;
-            const float p1 =
-                c0 + 1 < vlim ? exp2f(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, -m_used))
-                              : 0.f;
-            psum += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
-          }
-          // 32 columns = 64 B = four 16-byte chunks of k-block (c >> 1)
-          const uint32_t base = p_row + (c >> 1) * kHalfBytes;
+        for (int c = 0; c < 4; ++c)
+          if (c < n_chunks) {
+            const uint32_t base = p_row + (c >> 1) * kHalfBytes;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int cc = (c & 1) * 4 + q4;
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((cc ^ sw) << 4)),
-                         "r"(pk[4 * q4]), "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]),
-                         "r"(pk[4 * q4 + 3])
-                         : "memory");
-          }
-        }
-        l_run += psum;
-        // S[sb] is free for the block after next; P is complete
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar(S_EMPTY + sb));
-          mbar_arrive(bar(P_FULL));
-        }
-        if (b == ge.n_blocks - 1) {
-          // ---- epilogue: O / l -> global ----
-          mbar_wait(bar(O_FULL + ob), (n >> 1) & 1);
-          tc_fence_after();
-          const float inv = 1.0f / l_run;
-          const bool row_ok = q_own < ge.q_len;
-          __nv_bfloat16* dst = out + static_cast<size_t>(ge.q_start + q_own) * (hq * kHeadDim) +
-                               (ge.kvh * G + h_in) * kHeadDim;
-          const uint32_t o_addr = tmem_o + ob * 128 + lane_sel;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(o_addr + c * 32, v);
-            tmem_ld_wait();
-            if (row_ok) {
-              uint32_t o[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                o[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * inv,
-                                   __uint_as_float(v[2 * i + 1]) * inv);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                st_v4(dst + c * 32 + 8 * i,
-                      make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int cc = (c & 1) * 4 + q4;
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((cc ^ sw) << 4)),
+                           "r"(v[c][4 * q4]), "r"(v[c][4 * q4 + 1]), "r"(v[c][4 * q4 + 2]),
+                           "r"(v[c][4 * q4 + 3])
+                           : "memory");
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(O_EMPTY + ob));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(P_FULL));
+        flush_epilogue();   // the previous item's, if any: the tensor core is busy with this block
+        if (b == ge.n_blocks - 1) {
+          ep_pending = true;
+          ep_ob = ob;
+          ep_par = (n >> 1) & 1;
+          ep_inv = 1.0f / l_run;
+          ep_row_ok = q_own < ge.q_len;
+          ep_dst = out + static_cast<size_t>(ge.q_start + q_own) * (hq * kHeadDim) +
+                   (ge.kvh * G + h_in) * kHeadDim;
         }
       }
     }
+    flush_epilogue();
   }
 
   tc_fence_before();

@@ -19,7 +19,7 @@ import torch
 from . import _lib as L
 from . import modelspec as MS
 from . import vocab as VB
-from .schema_fsm import ByteDFA, FsmLimits, compile_schema
+from .schema_fsm import ByteDFA, FsmLimits, compile_schema, compile_thinking
 from .unicode_tables import class_table
 
 c_i32p = C.POINTER(C.c_int32)
@@ -388,14 +388,18 @@ class LocalEngine:
             self._h = None
 
     # ---- the hot path -----------------------------------------------------
-    def _template_tokens(self, system_prompt: Optional[str]):
-        key = (system_prompt, self.spec.embedding_model)
+    def _template_tokens(self, system_prompt: Optional[str], thinking: bool = False):
+        key = (system_prompt, self.spec.embedding_model, bool(thinking))
         if key not in self._tpl_cache:
             tpl = (VB.embedding_template(self.spec.family) if self.spec.embedding_model
                    else VB.chat_template(self.spec.family, system_prompt,
-                                         getattr(self, "empty_think_block", False)))
+                                         getattr(self, "empty_think_block", False)
+                                         and not thinking))
+            suffix = list(tpl.suffix)
+            if thinking and not self.spec.embedding_model:
+                suffix += ["<think>", "\n"]     # a thinking turn opens its reasoning block
             pre = np.asarray(self.tokenizer.encode_pieces(tpl.prefix), dtype=np.int32)
-            suf = np.asarray(self.tokenizer.encode_pieces(tpl.suffix), dtype=np.int32)
+            suf = np.asarray(self.tokenizer.encode_pieces(suffix), dtype=np.int32)
             self._tpl_cache[key] = (pre, suf)
         return self._tpl_cache[key]
 
@@ -424,21 +428,31 @@ class LocalEngine:
         self._jump_cache[key] = plan
         return plan
 
-    def compile_schema(self, schema: Dict[str, Any], limits: Optional[FsmLimits] = None) -> ByteDFA:
+    def compile_schema(self, schema: Optional[Dict[str, Any]], limits: Optional[FsmLimits] = None,
+                       thinking_chars: Optional[int] = None) -> ByteDFA:
+        """output_schema -> byte automaton (cached).  `thinking_chars`: the automaton of a
+        thinking model's turn instead — free reasoning of at most that many characters, the
+        closing `</think>` line, then the schema instance (or free text when schema is None)."""
         import json
-        key = json.dumps(schema, sort_keys=True) + repr(limits)
+        key = json.dumps(schema, sort_keys=True) + repr(limits) + repr(thinking_chars)
         if key not in self._fsm_cache:
-            self._fsm_cache[key] = compile_schema(schema, limits)
+            self._fsm_cache[key] = (compile_schema(schema, limits) if thinking_chars is None
+                                    else compile_thinking(schema, limits, thinking_chars))
         return self._fsm_cache[key]
 
     def _job_options(self, job: "JobC", system_prompt, json_schema, max_new_tokens, ignore_eos,
                      truncate_rows, share_prefix, fsm_limits, jump_forward, temperature, top_k,
-                     top_p, seed, seed_per_row):
+                     top_p, seed, seed_per_row, thinking_chars=None):
         """Fill the host-side fields of an sb200_job (prompt framing, schema automaton, jump-forward
         plan, sampling).  Returns (dfa, plan, keep) — `keep` holds the arrays the job points at."""
         emb_mode = self.spec.embedding_model
-        pre, suf = self._template_tokens(system_prompt)
-        dfa = self.compile_schema(json_schema, fsm_limits) if json_schema is not None else None
+        thinking = thinking_chars is not None and not emb_mode
+        pre, suf = self._template_tokens(system_prompt, thinking)
+        dfa = None
+        if thinking:
+            dfa = self.compile_schema(json_schema, fsm_limits, int(thinking_chars))
+        elif json_schema is not None:
+            dfa = self.compile_schema(json_schema, fsm_limits)
         plan = None
         if dfa is not None and jump_forward and not emb_mode:
             # jump-forward decoding: bytes the automaton forces are not the model's choice —
@@ -477,7 +491,8 @@ class LocalEngine:
                      return_first_logits: bool = False, jump_forward: bool = True,
                      temperature: float = 0.0, top_k: int = 0, top_p: float = 1.0, seed: int = 0,
                      seed_per_row: bool = False, return_logprobs: bool = False,
-                     row_ids: Optional[Sequence[int]] = None) -> Dict[str, Any]:
+                     row_ids: Optional[Sequence[int]] = None,
+                     thinking_chars: Optional[int] = None) -> Dict[str, Any]:
         """Phase B of the hot path, HBM to HBM: a device-resident Arrow column (uint8 bytes +
         int64 offsets[n_rows+1]) -> tokenise -> prefill/decode (+mask) -> detokenise ->
         device-resident results (`d_bytes`/`d_boff`, `flat`/`ooff` tokens, `d_emb`, ...).
@@ -504,7 +519,7 @@ class LocalEngine:
             dfa, plan, keep = self._job_options(job, system_prompt, json_schema, max_new_tokens,
                                                 ignore_eos, truncate_rows, share_prefix, fsm_limits,
                                                 jump_forward, temperature, top_k, top_p, seed,
-                                                seed_per_row)
+                                                seed_per_row, thinking_chars)
             job.row_tokens_dev, job.row_tok_off_dev = d_tok.data_ptr(), d_toff.data_ptr()
             job.row_tok_off, job.n_rows = _np_ptr(toff, c_i64p), n_rows
             job.out_tokens_dev = L.ptr(d_out)
@@ -596,7 +611,8 @@ class LocalEngine:
                  jump_forward: bool = True, temperature: float = 0.0, top_k: int = 0,
                  top_p: float = 1.0, seed: int = 0, seed_per_row: bool = False,
                  return_logprobs: bool = False,
-                 row_ids: Optional[Sequence[int]] = None) -> GenerationResult:
+                 row_ids: Optional[Sequence[int]] = None,
+                 thinking_chars: Optional[int] = None) -> GenerationResult:
         """The whole hot path for one frame column.  Three phases, timed separately:
           A  host -> HBM   : rows -> Arrow blob, template/schema compile (cached), H2D copy
           B  device        : tokenize, prefill/decode (+mask), detokenize — HBM to HBM
@@ -617,9 +633,9 @@ class LocalEngine:
                                     else None, {"n_rows": 0, "input_tokens": 0,
                                                 "output_tokens": 0, "rows_done": 0})
         # template / schema compilation (cached) belongs to the host phase
-        self._template_tokens(system_prompt)
-        if json_schema is not None:
-            self.compile_schema(json_schema, fsm_limits)
+        self._template_tokens(system_prompt, thinking_chars is not None)
+        if json_schema is not None or thinking_chars is not None:
+            self.compile_schema(json_schema, fsm_limits, thinking_chars)
         with torch.cuda.device(dev):
             d_text = (torch.from_numpy(np.ascontiguousarray(data)).to(dev) if n_bytes
                       else torch.zeros(1, dtype=torch.uint8, device=dev))
@@ -635,7 +651,8 @@ class LocalEngine:
                                   return_first_logits=return_first_logits,
                                   jump_forward=jump_forward, temperature=temperature, top_k=top_k,
                                   top_p=top_p, seed=seed, seed_per_row=seed_per_row,
-                                  return_logprobs=return_logprobs, row_ids=row_ids)
+                                  return_logprobs=return_logprobs, row_ids=row_ids,
+                                  thinking_chars=thinking_chars)
             t_b = time.perf_counter()
             # ---- phase C ---------------------------------------------------------
             outputs = out_tokens = emb = None
@@ -671,7 +688,8 @@ def _infer_one_call(self, rows, system_prompt: Optional[str] = None,
                     top_p: float = 1.0, seed: int = 0, seed_per_row: bool = False,
                     return_logprobs: bool = False, return_tokens: bool = True,
                     progress: Optional[Callable[[int, int, int], None]] = None,
-                    profile: bool = False) -> GenerationResult:
+                    profile: bool = False,
+                    thinking_chars: Optional[int] = None) -> GenerationResult:
     """The same job through `sb200_infer_text`: ONE C-ABI call with host buffers in and out
     (what a non-Python host would bind; the SDK's infer() and bench.py's `e2e` use it).
     `generate` is the phased form of the same work; the results are identical.  The call times
@@ -688,7 +706,8 @@ def _infer_one_call(self, rows, system_prompt: Optional[str] = None,
     job = JobC()
     dfa, plan, keep = self._job_options(job, system_prompt, json_schema, max_new_tokens,
                                         ignore_eos, truncate_rows, share_prefix, fsm_limits,
-                                        jump_forward, temperature, top_k, top_p, seed, seed_per_row)
+                                        jump_forward, temperature, top_k, top_p, seed, seed_per_row,
+                                        thinking_chars)
     cb = PROGRESS_FN(lambda r, i, o, u: progress(r, i, o)) if progress else PROGRESS_FN()
     job.progress = cb
     job.profile = int(profile)

@@ -1153,3 +1153,42 @@ def compile_schema(schema: Dict[str, Any], limits: Optional[FsmLimits] = None) -
     comp = _Compiler(schema, limits or FsmLimits())
     frag = comp.node(schema)
     return _determinise(comp.b.n, frag[0], frag[1])
+
+
+THINK_CLOSE = b"</think>\n\n"
+
+
+def compile_thinking(schema: Optional[Dict[str, Any]], limits: Optional[FsmLimits] = None,
+                     think_chars: int = 128) -> ByteDFA:
+    """Automaton of a thinking model's turn: up to `think_chars` characters of free reasoning
+    (any text without '<'), the closing `</think>` line, then the content — an instance of
+    `schema`, or free text when there is none.  The reference reports such outputs as
+    `{"content": ..., "reasoning_content": ...}` (sutro/sdk.py:1155-1164); the cap plays the
+    role FsmLimits plays for strings: with it every row reaches its content."""
+    lim = limits or FsmLimits()
+    comp = _Compiler(schema if isinstance(schema, dict) else {}, lim)
+    b = comp.b
+    plain = _mask(0x09, 0x0A, (0x20, 0x3B), (0x3D, 0x7E))
+
+    def text_char(allow_lt: bool):
+        parts = [b.bset(plain | (_mask(0x3C) if allow_lt else 0))]
+        for lo, hi in ((0x80, 0xD7FF), (0xE000, _MAX_CP)):
+            for seq in _utf8_sequences(lo, hi):
+                parts.append(b.seq(*[b.bset(_mask((x, y))) for x, y in seq]))
+        return b.alt(*parts)
+    reasoning = b.rep(lambda: text_char(False), 0, int(think_chars))
+    close = b.lit(THINK_CLOSE)
+    if schema is not None:
+        content = comp.node(schema)
+    else:
+        content = b.star(lambda: text_char(True))
+    frag = b.seq(reasoning, close, content)
+    return _determinise(b.n, frag[0], frag[1])
+
+
+def split_thinking(text: str):
+    """-> (reasoning_content, content) of a thinking turn produced under compile_thinking."""
+    head, sep, tail = text.partition("</think>")
+    if not sep:
+        return text.strip(), ""
+    return head.strip(), tail.lstrip("\n")

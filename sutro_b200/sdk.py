@@ -133,6 +133,10 @@ class Sutro(Templates, BaseSutroClient):
             print(to_colored_text(msg, state))
 
     def _engine(self, model: str):
+        base = model[:-len("-thinking")] if str(model).endswith("-thinking") else model
+        if model not in self._engines and model not in self.model_paths and (
+                base in self._engines or base in self.model_paths):
+            model = base          # "<model>-thinking" is the same weights, another turn format
         if model not in self._engines and model in self.model_paths:
             from .pretrained import load_pretrained
             if len(self.devices) > 1:
@@ -141,6 +145,8 @@ class Sutro(Templates, BaseSutroClient):
             self._say(f"Loading {model} from {self.model_paths[model]} on cuda:{self.devices[0]}")
             self._engines[model] = load_pretrained(self.model_paths[model], self.devices[0],
                                                    name=model, **self.engine_options)
+        if model not in self._engines:
+            model = base
         if model not in self._engines:
             from .engine import LocalEngine, MultiGpuEngine
             where = ", ".join(f"cuda:{d}" for d in self.devices)
@@ -156,12 +162,16 @@ class Sutro(Templates, BaseSutroClient):
         return self._engines[model]
 
     @staticmethod
-    def _default_max_new_tokens(eng, json_schema) -> int:
+    def _default_max_new_tokens(eng, json_schema, thinking_chars=None) -> int:
         """Output budget when sampling_params names none.  Schema jobs: the longest string the
         schema's automaton accepts (every token is at least one byte), so a constrained row
         can always close its object — a row cut mid-object would not be JSON.  Free text: 512."""
         spec = getattr(eng, "spec", None)
         cap = max(16, getattr(spec, "max_position", 4096) // 2)
+        if thinking_chars is not None and hasattr(eng, "compile_schema"):
+            longest = eng.compile_schema(json_schema, None, int(thinking_chars)).longest_path()
+            return int(min(max(longest, 8), cap)) if longest is not None else \
+                int(min(512 + 4 * int(thinking_chars), cap))
         if json_schema is not None and hasattr(eng, "compile_schema"):
             longest = eng.compile_schema(json_schema).longest_path()
             if longest is not None:
@@ -219,7 +229,7 @@ class Sutro(Templates, BaseSutroClient):
         # the local engine understands the usual keys and rejects the rest loudly.
         sp = dict(sampling_params or {})
         known = {"temperature", "top_p", "top_k", "seed", "random_seed", "max_tokens",
-                 "max_new_tokens", "ignore_eos"}
+                 "max_new_tokens", "ignore_eos", "max_thinking_chars"}
         unknown = sorted(set(sp) - known)
         if unknown:
             raise ValueError(f"unsupported sampling_params for the local engine: {unknown} "
@@ -254,8 +264,13 @@ class Sutro(Templates, BaseSutroClient):
                 self._say(f"✔ Cost estimates retrieved for job {job.job_id}: $0.0 "
                           f"({job.stats['input_tokens']} input tokens)", "success")
                 return job.job_id
+            # "<model>-thinking" (sutro/common.py:28-32): reason first, answer after </think>; the
+            # job's outputs are {"content", "reasoning_content"} objects (sutro/sdk.py:1155-1164)
+            thinking = None
+            if str(model).endswith("-thinking") and not getattr(eng.spec, "embedding_model", False):
+                thinking = int(sp.get("max_thinking_chars", 128))
             if max_new is None:
-                max_new = self._default_max_new_tokens(eng, json_schema)
+                max_new = self._default_max_new_tokens(eng, json_schema, thinking)
             t0 = time.perf_counter()
             stream = None
             if self.on_progress is not None or (stay_attached and self.verbose):
@@ -266,6 +281,8 @@ class Sutro(Templates, BaseSutroClient):
                       truncate_rows=truncate_rows, temperature=temperature, top_k=top_k,
                       top_p=top_p, seed=seed, seed_per_row=bool(random_seed_per_input),
                       return_logprobs=True, progress=stream)
+            if thinking is not None:
+                kw["thinking_chars"] = thinking
             res = self._dispatch(eng, input_data, kw)
             if res is None:          # a non-source rank of a row-sharded job: nothing to report
                 job.status = JobStatus.SUCCEEDED
@@ -300,6 +317,19 @@ class Sutro(Templates, BaseSutroClient):
             job.outputs = list(res.embeddings)
         else:
             job.outputs = res.outputs
+            if thinking is not None and job.outputs is not None:
+                from .schema_fsm import split_thinking
+                shaped = []
+                for text in job.outputs:
+                    reasoning, content = split_thinking(text)
+                    if json_schema is not None:
+                        try:
+                            content = json.loads(content)
+                        except ValueError:
+                            pass       # cut by max_tokens: keep the text
+                    shaped.append(json.dumps({"content": content, "reasoning_content": reasoning},
+                                             ensure_ascii=False))
+                job.outputs = shaped
         job.status = JobStatus.SUCCEEDED
         tps = (res.stats.get("input_tokens", 0) + res.stats.get("output_tokens", 0)) / max(dt, 1e-9)
         self._say(f"Input tokens processed: {res.stats.get('input_tokens', 0)}, Output tokens "

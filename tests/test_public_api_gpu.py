@@ -81,6 +81,26 @@ def test_templates_run_on_the_real_engine():
     assert vecs.shape[0] == 6 and np.allclose(np.linalg.norm(vecs, axis=1), 1.0, atol=1e-3)
 
 
+def test_thinking_model_outputs_content_and_reasoning():
+    """"<model>-thinking": reasoning first (capped), then the schema-constrained answer; the
+    job reports {"content", "reasoning_content"} (sutro/sdk.py:1155-1164, common.py:28-32)."""
+    import sutro_b200 as so
+    so.configure(engine_options=OPTS, verbose=False, cache_dir="/tmp/sb200-test-cache")
+    rows = synth.README_REVIEWS + synth.product_reviews(5, seed=8)
+    job = so.infer(rows, model="tiny-qwen3-thinking", system_prompt=synth.README_SYSTEM_PROMPT,
+                   output_schema=Sentiment, sampling_params={"max_thinking_chars": 24},
+                   stay_attached=False)
+    raw = so.get_job_results(job, unpack_json=False)["inference_result"]
+    for text in raw:
+        obj = json.loads(text)
+        assert sorted(obj) == ["content", "reasoning_content"]
+        Sentiment.model_validate(obj["content"])
+        assert len(obj["reasoning_content"]) <= 24 and "<" not in obj["reasoning_content"]
+    df = so.get_job_results(job)
+    assert set(df["sentiment"]) <= {"positive", "neutral", "negative"}
+    assert "reasoning_content" in df.columns and "content" not in df.columns
+
+
 def test_arrow_helpers_match_numpy():
     """sb200_rows_select / sb200_compact_rows (the kernels behind row sharding, the ordered
     gather and output compaction) against numpy — bit-exact."""

@@ -296,3 +296,21 @@ def test_longest_path_bounds_every_accepted_string():
     assert d.longest_path() == len("[99,99,99]")
     d = compile_schema({"type": "string"}, FsmLimits(max_string_chars=4))
     assert d.longest_path() == 2 + 4 * 6        # four \\uXXXX escapes between the quotes
+
+
+def test_thinking_turn_automaton():
+    """`<model>-thinking`: free reasoning (capped, no '<'), the closing </think> line, then the
+    schema instance or free text (reference output shape: sutro/sdk.py:1155-1164)."""
+    from sutro_b200.schema_fsm import compile_thinking, split_thinking
+    sch = {"type": "object", "properties": {"sentiment": {"type": "string", "enum": ["a", "b"]}}}
+    d = compile_thinking(sch, None, 16)
+    assert d.matches(b'hm, ok\n</think>\n\n{"sentiment":"a"}')
+    assert d.matches(b'</think>\n\n{"sentiment":"b"}')                     # empty reasoning
+    assert not d.matches(b'{"sentiment":"a"}')                             # the block is not optional
+    assert not d.matches(b'x<y</think>\n\n{"sentiment":"a"}')              # '<' only opens the close tag
+    assert not d.matches(b'12345678901234567</think>\n\n{"sentiment":"a"}')   # 17 > 16 characters
+    assert d.longest_path() == 16 * 4 + len("</think>\n\n") + len('{"sentiment":"a"}')
+    free = compile_thinking(None, None, 8)
+    assert free.matches("é ok</think>\n\nfree <text> here".encode()) and free.longest_path() is None
+    assert split_thinking('hm, ok\n</think>\n\n{"sentiment":"a"}') == ("hm, ok", '{"sentiment":"a"}')
+    assert split_thinking("never closed") == ("never closed", "")

@@ -502,3 +502,31 @@ def test_files_and_frame_columns_travel_as_arrow(tmp_path):
     assert eng.calls[-1][0] == ["a: 1", ": 2", "c: 3"]
     with pytest.raises(ValueError, match="Column name must be specified"):
         c.infer(str(tmp_path / "f.parquet"), model="qwen-3-4b")
+
+
+def test_thinking_models_report_content_and_reasoning():
+    """"<model>-thinking" (sutro/common.py:28-32): outputs are {"content", "reasoning_content"}
+    objects and get_job_results fans the content's keys out (sutro/sdk.py:1155-1164)."""
+    class ThinkEngine(StubEngine):
+        class spec:
+            max_position = 4096
+            embedding_model = False
+
+        def generate(self, rows, **kw):
+            self.calls.append((list(rows), kw))
+            outs = [f"row {i} looks fine\n</think>\n\n" + json.dumps({"sentiment": f"s{i}"})
+                    for i in range(len(rows))]
+            return GenerationResult(outs, None, None, {"input_tokens": 1, "output_tokens": 1})
+    c = Sutro(verbose=False, cache_dir="/tmp/sb200-test-cache")
+    eng = ThinkEngine()
+    c.register_engine("qwen-3-4b", eng)
+    job = c.infer(["a", "b"], model="qwen-3-4b-thinking", output_schema=Sentiment,
+                  sampling_params={"max_thinking_chars": 40, "max_tokens": 99}, stay_attached=False)
+    assert eng.calls[-1][1]["thinking_chars"] == 40
+    raw = c.get_job_results(job, unpack_json=False)["inference_result"]
+    assert json.loads(raw[0]) == {"content": {"sentiment": "s0"}, "reasoning_content": "row 0 looks fine"}
+    df = c.get_job_results(job)
+    assert list(df["sentiment"]) == ["s0", "s1"] and list(df["reasoning_content"])[1] == "row 1 looks fine"
+    # a non-thinking model name does not ask for a thinking turn
+    c.infer(["a"], model="qwen-3-4b", output_schema=Sentiment, stay_attached=False)
+    assert "thinking_chars" not in eng.calls[-1][1]
