@@ -91,6 +91,12 @@ SB_DEVICE void tc_block(const TcGeom& g, int b, bool& is_pre, int& j0, int& n16)
   n16 = (limit + 15) & ~15;
 }
 
+SB_DEVICE float ex2_approx(float x) {   // MUFU.EX2: 2^x, flushes denormals (x <= -126 -> 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int G>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, head, token) over qkv
@@ -340,14 +346,26 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
-        float mx = -INFINITY;
+        // One softmax warp per SM sub-partition: nothing hides ALU latency but ILP, and every
+        // instruction counts.  So (a) chunks that are valid for every row of the warp (all but
+        // the diagonal one: lane 0 holds the warp's smallest limit, limits grow with the lane)
+        // take a path without per-element predicates, (b) max and sum run on four independent
+        // accumulators, (c) exp2 is the bare MUFU (ex2.approx.ftz).
+        const int vmin = __shfl_sync(0xffffffffu, vlim, 0);
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c < n_chunks) {
+            if (c * 32 + 32 <= vmin) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < vlim) mx = fmaxf(mx, __uint_as_float(v[c][i]));
+              for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < vlim) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
+            }
           }
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         mx *= scale_log2;  // scale > 0: max commutes with the scaling
         // ---- running max with lazy rescale ----
         float alpha = 1.f;
@@ -356,30 +374,40 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
           m_used = (mx == -INFINITY) ? 0.f : mx;
           l_run = 0.f;
         } else if (mx > m_used + kRescaleThreshold) {
-          alpha = exp2f(m_used - mx);
+          alpha = ex2_approx(m_used - mx);
           m_used = mx;
           l_run *= alpha;
           need = true;
         }
         // ---- P = exp2(s*scale - m) -> bf16 (registers) ----
-        float psum = 0.f;
+        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float neg_m = -m_used;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c < n_chunks) {
+            if (c * 32 + 32 <= vmin) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {   // packed pairs overwrite the scores in place
-              const int c0 = c * 32 + 2 * i;
-              const float p0 = c0 < vlim
-                                   ? exp2f(fmaf(__uint_as_float(v[c][2 * i]), scale_log2, -m_used))
-                                   : 0.f;
-              const float p1 =
-                  c0 + 1 < vlim
-                      ? exp2f(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2, -m_used))
-                      : 0.f;
-              psum += p0 + p1;
-              v[c][i] = pack_bf16x2(p0, p1);
+              for (int i = 0; i < 16; ++i) {   // packed pairs overwrite the scores in place
+                const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), scale_log2, neg_m));
+                const float p1 =
+                    ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2, neg_m));
+                ps4[i & 3] += p0 + p1;
+                v[c][i] = pack_bf16x2(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int c0 = c * 32 + 2 * i;
+                float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), scale_log2, neg_m));
+                float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2, neg_m));
+                p0 = c0 < vlim ? p0 : 0.f;
+                p1 = c0 + 1 < vlim ? p1 : 0.f;
+                ps4[i & 3] += p0 + p1;
+                v[c][i] = pack_bf16x2(p0, p1);
+              }
             }
           }
+        const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
         l_run += psum;
         // the previous block's PV must have retired before O is rescaled or P is overwritten
         mbar_wait(bar(P_EMPTY), (g & 1) ^ 1);

@@ -23,6 +23,7 @@
 //                  (gate/up weights interleaved row-wise; output has N/2 columns)
 //   STORE_F32      D = acc                             (lm_head logits)
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -830,7 +831,16 @@ int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* 
     set_last_error("gemm_bf16_tn: unsupported shape M=%d N=%d K=%d a_rows=%d", M, N, K, a_rows);
     return -1;
   }
-  if (block_n == 0) block_n = gemm_pick_block_n(M, N);
+  if (block_n == 0) {
+    block_n = gemm_pick_block_n(M, N);
+    // A/B knob: SB200_GEMM_SWIGLU_BN=256 runs the gate/up projection on the one-CTA 128x256
+    // kernel at large M (tools/gemm_bench.py measured it ahead of the CTA pair in isolation)
+    static const int swiglu_bn = [] {
+      const char* e = getenv("SB200_GEMM_SWIGLU_BN");
+      return e ? atoi(e) : 0;
+    }();
+    if (swiglu_bn > 0 && epilogue == EPI_SWIGLU_BF16 && block_n == 512) block_n = swiglu_bn;
+  }
   if (block_n != 64 && block_n != 128 && block_n != 256 && block_n != 512 && block_n != 514 &&
       block_n != 516) {
     set_last_error("gemm_bf16_tn: block_n must be 64/128/256/512(CTA pair), got %d", block_n);

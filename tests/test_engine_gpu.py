@@ -383,14 +383,15 @@ def test_embedding_model_matches_oracle():
 
 
 def test_row_order_is_preserved_with_more_rows_than_slots():
-    spec, w, v, eng = build("tiny-qwen3", max_slots=4, max_prefill_tokens=256, min_admit_rows=1)
+    spec, w, v, eng = build("tiny-qwen3", max_slots=4, max_prefill_tokens=384, min_admit_rows=1)
     rows = synth.product_reviews(30, seed=5)
     res = eng.generate(rows, json_schema=SentimentEnum.model_json_schema(), max_new_tokens=32,
                        return_tokens=True)
     one_by_one = [eng.generate([r], json_schema=SentimentEnum.model_json_schema(),
                                max_new_tokens=32, return_tokens=True).out_tokens[0]
                   for r in rows[:10]]
-    assert sum(a == b for a, b in zip(res.out_tokens[:10], one_by_one)) >= 9
+    # batch-invariant kernels: a row decoded alone equals the same row decoded in a batch
+    assert res.out_tokens[:10] == one_by_one
     assert res.stats["rows_done"] == 30 and res.stats["decode_steps"] > 0
 
 

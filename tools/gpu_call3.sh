@@ -2,8 +2,13 @@
 set -u
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_real_size.jsonl
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py tests/test_zy_real_size_parity_gpu.py tests/test_c_host_gpu.py -q --timeout 900 -p no:cacheprovider \
-   -k "tile_configurations or row_order or real_size or c_program" 2>&1 | tail -80 > gpurun_out/c3_pytest.txt
+# the rewritten softmax branch of the tcgen05 attention first: stop here if it is wrong
+timeout -k 10 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "dense" -p no:cacheprovider 2>&1 | tail -8
+if [ ${PIPESTATUS[0]} -ne 0 ]; then echo "DENSE ATTENTION TESTS FAILED - stopping"; exit 1; fi
+timeout 120 python tools/attn_bench.py 2>&1 | tail -4
+timeout 120 python tools/attn_bench.py --new 512 --past 0 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_engine_gpu.py tests/test_zy_real_size_parity_gpu.py tests/test_c_host_gpu.py tests/test_public_api_gpu.py -q --timeout 900 -p no:cacheprovider \
+   -k "tile_configurations or row_order or real_size or c_program or public or thinking or templates" 2>&1 | tail -80 > gpurun_out/c3_pytest.txt
 tail -70 gpurun_out/c3_pytest.txt
 SB200_QKV_DENSE=1 timeout 120 python tools/qkv_epi_bench.py 2>&1 | tail -3
 SB200_QKV_DENSE=0 timeout 120 python tools/qkv_epi_bench.py 2>&1 | head -1
