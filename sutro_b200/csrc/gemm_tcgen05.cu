@@ -833,13 +833,17 @@ int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* 
   }
   if (block_n == 0) {
     block_n = gemm_pick_block_n(M, N);
-    // A/B knob: SB200_GEMM_SWIGLU_BN=256 runs the gate/up projection on the one-CTA 128x256
-    // kernel at large M (tools/gemm_bench.py measured it ahead of the CTA pair in isolation)
+    // The wide gate/up projection (N = 2*d_ff) runs on the one-CTA 128x256 kernel: measured
+    // ahead of the CTA pair on that shape both in isolation (1553 vs 1502 TFLOP/s at M = 32768)
+    // and inside the benchmark step (-1.7 % GEMM time).  Every tile shape accumulates in the
+    // same order, so this choice changes no result.  SB200_GEMM_SWIGLU_BN=512 restores the pair.
     static const int swiglu_bn = [] {
       const char* e = getenv("SB200_GEMM_SWIGLU_BN");
-      return e ? atoi(e) : 0;
+      return e ? atoi(e) : 256;
     }();
-    if (swiglu_bn > 0 && epilogue == EPI_SWIGLU_BF16 && block_n == 512) block_n = swiglu_bn;
+    if (epilogue == EPI_SWIGLU_BF16 && block_n == 512 && N >= 8192 &&
+        (swiglu_bn == 256 || swiglu_bn == 512))
+      block_n = swiglu_bn;
   }
   if (block_n != 64 && block_n != 128 && block_n != 256 && block_n != 512 && block_n != 514 &&
       block_n != 516) {
