@@ -91,6 +91,34 @@ def load_tokenizer_json(path: str, family: str, vocab_size: Optional[int] = None
             continue          # a merge whose parts or result are not tokens can never apply
         merges.append((int(r2e[real_vocab[a]]), int(r2e[real_vocab[b]])))
         merged_ids.append(int(r2e[real_vocab[ab]]))
+    if model.get("ignore_merges"):
+        # `ignore_merges` (Llama-3 files set it): a pre-token that is itself in the vocabulary
+        # is emitted as that token without running the merges.  The GPU BPE always merges, so
+        # the flag is honoured by proof: it is a no-op exactly when merging every vocabulary
+        # string reproduces its own token — checked here for all of them; otherwise refuse.
+        rank = {pair: (i, merged_ids[i]) for i, pair in reversed(list(enumerate(merges)))}
+        bad = 0
+        for e, tb in enumerate(token_bytes):
+            if len(tb) < 2:
+                continue
+            seq = list(tb)
+            while len(seq) > 1:
+                best, bi = None, -1
+                for i in range(len(seq) - 1):
+                    r = rank.get((seq[i], seq[i + 1]))
+                    if r is not None and (best is None or r[0] < best[0]):
+                        best, bi = r, i
+                if best is None:
+                    break
+                seq[bi:bi + 2] = [best[1]]
+            if seq != [e]:
+                bad += 1
+        if bad and os.environ.get("SB200_ALLOW_IGNORE_MERGES_MISMATCH") != "1":
+            raise ValueError(
+                f"{path}: model.ignore_merges is true and {bad} vocabulary entries are not what "
+                "their merges produce — a word equal to one of those entries would get other ids "
+                "here than under `tokenizers` (same text after decoding, different tokens than the "
+                "model was trained on).  Set SB200_ALLOW_IGNORE_MERGES_MISMATCH=1 to load anyway.")
     specials = {name: int(r2e[i]) for name, i in added.items()}
     need = "<|im_end|>" if family == "qwen3" else "<|eot_id|>"
     if need not in specials:

@@ -166,3 +166,39 @@ def test_real_pretokenizer_patterns_and_normalizers(tmp_path):
         PT.load_tokenizer_json(path, "qwen3")
     from sutro_b200.engine import _nfc_rows
     assert _nfc_rows(["é", None, "plain", 3]) == ["é", None, "plain", 3]
+
+
+def test_ignore_merges_is_honoured_by_proof_or_refused(tmp_path, monkeypatch):
+    """Llama-3 tokenizer files set model.ignore_merges (a pre-token that is itself a vocabulary
+    entry is emitted whole).  The GPU BPE always merges, so the loader PROVES the flag is a no-op
+    — merging every vocabulary string must reproduce its own token — and otherwise refuses to
+    load (or loads with an explicit opt-in), never serving other ids silently."""
+    v = VB.build_vocab("llama", 2048, seed=0, n_trained=600)
+    hf = gpt2_ordered_tokenizer(v)
+    path = str(tmp_path / "tokenizer.json")
+    hf.save(path)
+    tj = json.load(open(path))
+    assert PT.load_tokenizer_json(path, "llama").vocab_size > 0      # flag absent: loads
+    tj["model"]["ignore_merges"] = True
+    json.dump(tj, open(path, "w"))
+    # does merging reproduce every entry of this vocabulary?  (count with the oracle's BPE)
+    monkeypatch.setenv("SB200_ALLOW_IGNORE_MERGES_MISMATCH", "1")
+    loaded = PT.load_tokenizer_json(path, "llama")
+    ref = RefTokenizer(loaded)
+    mismatches = sum(1 for e, tb in enumerate(loaded.token_bytes)
+                     if len(tb) >= 2 and ref._bpe(tb) != [e])
+    monkeypatch.delenv("SB200_ALLOW_IGNORE_MERGES_MISMATCH")
+    if mismatches:
+        with pytest.raises(ValueError, match=f"ignore_merges is true and {mismatches} vocabulary"):
+            PT.load_tokenizer_json(path, "llama")
+    else:
+        assert PT.load_tokenizer_json(path, "llama").vocab_size == loaded.vocab_size
+    # a vocabulary reduced to its byte tokens and first merges is consistent: accepted
+    keep = dict(list(tj["model"]["vocab"].items())[:256 + 40])
+    tj["model"]["vocab"] = keep
+    tj["model"]["merges"] = [m for m in tj["model"]["merges"]
+                             if "".join(m if isinstance(m, list) else m.split(" ")) in keep][:40]
+    tj["added_tokens"] = [dict(a, id=len(keep) + i) for i, a in enumerate(tj["added_tokens"])]
+    json.dump(tj, open(path, "w"))
+    small = PT.load_tokenizer_json(path, "llama")
+    assert len(small.merges) > 0
