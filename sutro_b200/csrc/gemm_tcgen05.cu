@@ -180,16 +180,35 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
              rm.r * kHeadDim;
     swz = rm.r & 7;
   }
+  // Packed bf16x2 arithmetic: a product of two bf16 values is exact in fp32, so HMUL2.BF16
+  // (one rounding) equals "fp32 multiply, round to bf16" — the rounding points of the unfused
+  // kernel (norm_rope.cu) and of the oracle; sums are HADD2.BF16 (exact sum, one rounding).
+  // Two elements per instruction and no unpack/repack: the epilogue is a third of its former
+  // instruction count, which is what keeps the fused QKV GEMM from being epilogue-bound.
+  // explicit .rn forms: ptxas must not contract mul + add/sub into one fused (singly rounded) FMA
+  auto mul2 = [](uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+  };
+  auto add2 = [](uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+  };
+  auto sub2 = [](uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+  };
 #pragma unroll
   for (int gg = 0; gg < 4; ++gg) {  // dims 8g..8g+7 of the low half and their +64 partners
     const int g = 4 * part + gg;
-    float lo[8], hi[8];
+    uint32_t lo[4], hi[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 a = unpack_bf16x2(pk[4 * gg + j]);
-      const float2 b = unpack_bf16x2(pk[16 + 4 * gg + j]);
-      lo[2 * j] = a.x, lo[2 * j + 1] = a.y;
-      hi[2 * j] = b.x, hi[2 * j + 1] = b.y;
+      lo[j] = pk[4 * gg + j];
+      hi[j] = pk[16 + 4 * gg + j];
     }
     if (nw != nullptr) {
       const uint4 wl4 = *reinterpret_cast<const uint4*>(nw + 8 * g);
@@ -197,34 +216,26 @@ SB_DEVICE void qkv_head_epilogue(uint32_t tmem_head, const QkvEpiArgs& ea, const
       const uint32_t wl[4] = {wl4.x, wl4.y, wl4.z, wl4.w};
       const uint32_t wh[4] = {wh4.x, wh4.y, wh4.z, wh4.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 a = unpack_bf16x2(wl[j]), b = unpack_bf16x2(wh[j]);
-        lo[2 * j] = bf16_round(a.x * bf16_round(lo[2 * j] * rstd));
-        lo[2 * j + 1] = bf16_round(a.y * bf16_round(lo[2 * j + 1] * rstd));
-        hi[2 * j] = bf16_round(b.x * bf16_round(hi[2 * j] * rstd));
-        hi[2 * j + 1] = bf16_round(b.y * bf16_round(hi[2 * j + 1] * rstd));
+      for (int j = 0; j < 4; ++j) {   // w * bf16(x * rstd): rstd is fp32, so that product is fp32
+        const float2 a = unpack_bf16x2(lo[j]), b = unpack_bf16x2(hi[j]);
+        lo[j] = mul2(wl[j], pack_bf16x2(a.x * rstd, a.y * rstd));
+        hi[j] = mul2(wh[j], pack_bf16x2(b.x * rstd, b.y * rstd));
       }
     }
     if (is_q || is_k) {
+      // out[i] = x[i]*cos - x[i+64]*sin ; out[i+64] = x[i+64]*cos + x[i]*sin (bf16 op by op)
       const uint4 c4 = rm.cs[gg], s4 = rm.sn[gg];
       const uint32_t cu[4] = {c4.x, c4.y, c4.z, c4.w};
       const uint32_t su[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 c = unpack_bf16x2(cu[j]), sn = unpack_bf16x2(su[j]);
-        const float cc[2] = {c.x, c.y}, sv[2] = {sn.x, sn.y};
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float x = lo[2 * j + e], y = hi[2 * j + e];
-          lo[2 * j + e] = bf16_round(x * cc[e]) + bf16_round(-y * sv[e]);
-          hi[2 * j + e] = bf16_round(y * cc[e]) + bf16_round(x * sv[e]);
-        }
+        const uint32_t x = lo[j], y = hi[j];
+        lo[j] = sub2(mul2(x, cu[j]), mul2(y, su[j]));
+        hi[j] = add2(mul2(y, cu[j]), mul2(x, su[j]));
       }
     }
-    const uint4 olo = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]),
-                                 pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
-    const uint4 ohi = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]),
-                                 pack_bf16x2(hi[4], hi[5]), pack_bf16x2(hi[6], hi[7]));
+    const uint4 olo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    const uint4 ohi = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     st_v4(dst_lo + ((g ^ swz) << 3), olo);
     st_v4(dst_lo + (((g + 8) ^ swz) << 3), ohi);
     if (!is_q && ea.write_dense) {
@@ -726,9 +737,19 @@ int num_sms() {
   return cached[dev];
 }
 
-// Row-tiles per raster group: as many as keep the group's A slab (rows x K bf16) within
-// ~48 MB of the 126 MB L2, so A is read from HBM once and W once per group.
-int raster_group(int tile_rows, int K) {
+// Row-tiles per raster group.  A weight matrix that fits L2 with room to spare (<= 64 MB:
+// QKV, Wo, down) stays resident whatever the order, so narrow groups win — the CTAs of a wave
+// then share few A row-tiles and walk W together (measured at M=32768: GM 1-4 is 2-4 % faster
+// than wide groups, tools/gemm_raster_scan.py).  A larger W (gate/up, the LM head) is streamed:
+// there the group takes as many row-tiles as keep its A slab (rows x K bf16) within ~48 MB of
+// the 126 MB L2, so A is read from HBM once and W once per group.
+int raster_group(int tile_rows, int N, int K) {
+  static const int forced = [] {   // SB200_GEMM_GM: experiment knob (tools/gemm_raster_scan.py)
+    const char* e = getenv("SB200_GEMM_GM");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced > 0) return forced;
+  if (static_cast<long>(N) * K * 2 <= (64L << 20)) return 2;
   const long slab = 48L << 20;
   long gm = slab / (static_cast<long>(tile_rows) * K * 2);
   if (gm < 2) gm = 2;
@@ -749,7 +770,7 @@ int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* re
   const int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, gemm_threads<EPI>(), Cfg::kSmemBytes, stream>>>(
       tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd,
-      raster_group(kBlockM, K), ea);
+      raster_group(kBlockM, N, K), ea);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -766,7 +787,7 @@ int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* r
   const int clusters = std::min(tiles, num_sms() / 2);
   kern<<<2 * clusters, gemm_threads<EPI>(), k2SmemBytes(STAGES), stream>>>(
       tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd,
-      raster_group(256, K), ea);
+      raster_group(256, N, K), ea);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

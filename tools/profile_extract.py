@@ -31,8 +31,11 @@ KEYS = [
 
 
 def main(rep, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
+    if rep.endswith(".csv"):     # a raw page already exported on the GPU box (`ncu -i … --page raw --csv`)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {k: hdr.index(k) for k, _ in KEYS if k in hdr}
@@ -49,8 +52,9 @@ def main(rep, out):
                     continue
                 v = r[idx[k]]
                 if k == "Kernel Name":
-                    v = v.replace("(anonymous namespace)::", "").replace("sb::", "")
-                    v = v.split("(CUtensorMap")[0].split("(const ")[0][:80]
+                    v = v.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+                    v = v.replace("sb::", "").replace("void ", "")
+                    v = v.split("(CUtensorMap")[0].split("(const ")[0].split("(sb::")[0][:80]
                 vals.append(v)
             w.writerow(vals)
     print(out, len(rows) - 2, "launches")
