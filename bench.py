@@ -83,21 +83,25 @@ def peaks():
             "source": "fallback"}
 
 
-def ncu_traffic(csv_name: str):
-    """DRAM bytes (read + write) of one launch from a committed `ncu --set full` capture under
-    profiles/ (first launch row of the raw-page CSV), or None.  The capture is of one
-    representative launch of the kernel class, not of this run."""
+def ncu_traffic(csv_name: str, kernel: str):
+    """DRAM bytes (read + write) of one launch of `kernel` (substring of the kernel name) from a
+    committed `ncu --set full` capture under profiles/ (the per-launch summary
+    tools/profile_extract.py writes), or None.  The capture is of one representative launch of
+    the kernel class inside the same workload, not of this run."""
     try:
         import csv
         with open(os.path.join(ROOT, "profiles", csv_name), newline="") as f:
             rows = list(csv.reader(f))
-        hdr, units, first = rows[0], rows[1], rows[2]
+        hdr = rows[0]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        total = 0.0
-        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            i = hdr.index(key)
-            total += float(first[i]) * scale[units[i]]
-        return total
+        cols = []
+        for i, h in enumerate(hdr):
+            if h.startswith(("dram_read", "dram_write")):
+                cols.append((i, scale[h[h.index("[") + 1:h.index("]")]]))
+        for r in rows[1:]:
+            if kernel in r[0]:
+                return sum(float(r[i]) * k for i, k in cols)
+        return None
     except Exception:
         return None
 
@@ -668,10 +672,11 @@ def main():
                     "bound": "tensor", "achieved": kb["gemm_tflops"],
                     "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": kb["gemm_frac_of_sustained_peak"],
-                    "traffic": ncu_traffic("r01_ncu_gemm_gateup_raw.csv"),
-                    "traffic_note": "bytes of ONE gate-up GEMM launch (M~16k, N=19456, K=2560; "
-                                    "algorithmic ~503 MB) from the committed capture "
-                                    "profiles/r01_ncu_gemm_gateup_raw.csv, not from this run",
+                    "traffic": ncu_traffic("r02_ncu_prefill_step.csv", "gemm_bf16_tn_kernel<256, 2>"),
+                    "traffic_note": "bytes of ONE gate/up GEMM launch of a full prefill step "
+                                    "(M=32670, N=19456, K=2560; algorithmic 903 MB = A 167 + "
+                                    "W 100 + SwiGLU output 636) from the committed capture "
+                                    "profiles/r02_ncu_prefill_step.csv, not from this run",
                     "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                     "share_of_step": kb["share"]["gemm"],
                     "launches": prof["kernel_launches"]["gemm"],
@@ -681,7 +686,7 @@ def main():
                          "achieved": kb["attn_decode_gbs_non_shared_kv"], "peak": pk["hbm_gbs"],
                          "unit": "GB/s", "frac": kb["attn_decode_frac_of_hbm_peak"],
                          "bytes": "non-shared KV only (the shared system-prompt pages are L2 hits)",
-                         "traffic": ncu_traffic("r01_ncu_attn_decode_raw.csv"),
+                         "traffic": ncu_traffic("r02_ncu_decode_side.csv", "attn_decode_warp_kernel"),
                          "share_of_step": kb["attn_decode_share_of_step"],
                          "launches": prof["kernel_launches"]["attn_decode"],
                          "note": "the headline job barely decodes (jump-forward); the graded "

@@ -16,8 +16,8 @@
 // row's own blocks up to the tile's diagonal; the MMA N (and the PV K extent) is the valid
 // token count rounded up to 16, so short sequences do not pay for padding.
 //
-// Persistent CTA, 192 threads, one per SM, software-pipelined across blocks AND items:
-//   warp 4      TMA producer  Q tile (double-buffered), K and V rings (2 stages each)
+// Persistent CTA, 224 threads, one per SM, software-pipelined across blocks AND items:
+//   warps 4, 6  TMA producers Q tile (double-buffered) + K ring / V ring (2 stages each)
 //   warp 5      MMA issuer    S = Q K^T -> TMEM S[2];  O (+)= P V -> TMEM O[2]
 //   warps 0-3   softmax       thread == TMEM lane == tile row: tcgen05.ld S, running max with
 //                             lazy rescale (threshold 2^8), exp2, P -> shared memory (bf16,
@@ -39,7 +39,7 @@ namespace sb {
 
 namespace {
 
-constexpr int kTcThreads = 320;   // 2 softmax warpgroups (lanes) + TMA producer + MMA issuer
+constexpr int kTcThreads = 224;   // warps 0-3 softmax, 4 Q/K producer, 5 MMA issuer, 6 V producer
 constexpr int kBlk = 128;                    // KV tokens per block (TMEM S columns)
 constexpr int kHalfBytes = 128 * 128;        // [128 rows][64 bf16] = 16 KiB, one d-half / k-block
 constexpr int kTileBytes2 = 2 * kHalfBytes;  // 32 KiB: Q tile, K block, V block, P block
@@ -97,82 +97,6 @@ SB_DEVICE float ex2_approx(float x) {   // MUFU.EX2: 2^x, flushes denormals (x <
   return y;
 }
 
-// The two softmax warpgroups of a CTA work on different items at the same time ("lanes": lane
-// L takes the CTA's items L, L+2, ...).  Every role walks the SAME merged sequence of steps —
-// the two lanes' (item, block) streams interleaved round-robin, a lane that runs out of work
-// yielding its turns — so shared resources (K/V ring stage, the P buffer) are indexed by the
-// global step number and per-lane resources (Q, S, O) by the lane.
-template <int G>
-struct TcWalk {
-  const int32_t* items;
-  const int32_t* qs;
-  const int32_t* ql;
-  const int32_t* past;
-  int hkv, first, stride, total;
-  // per-lane state as scalars (a runtime-indexed array would live in local memory)
-  int k0, k1;            // next item index (in units of `stride`) of each lane
-  int cur0, cur1;        // the lane's current item
-  int nb0, nb1;          // ... and its number of KV blocks
-  int blk0, blk1;        // next block of the lane's current item; -1: no current item
-  uint32_t n0, n1;       // items started per lane
-  uint32_t s0, s1;       // steps taken per lane
-  uint32_t g;            // global step counter
-  int turn;
-
-  SB_DEVICE void init(const int32_t* items_, const int32_t* qs_, const int32_t* ql_,
-                      const int32_t* past_, int hkv_, int first_, int stride_, int total_) {
-    items = items_, qs = qs_, ql = ql_, past = past_, hkv = hkv_;
-    first = first_, stride = stride_, total = total_;
-    k0 = 0, k1 = 1;
-    cur0 = cur1 = 0;
-    nb0 = nb1 = 0;
-    blk0 = blk1 = -1;
-    n0 = n1 = s0 = s1 = 0;
-    g = 0;
-    turn = 0;
-  }
-  SB_DEVICE TcGeom geom(int L) const {
-    return tc_geom<G>(L ? cur1 : cur0, hkv, items, qs, ql, past);
-  }
-  SB_DEVICE bool lane_has_work(int L) const {
-    if ((L ? blk1 : blk0) >= 0) return true;
-    return first + (L ? k1 : k0) * stride < total;
-  }
-  // next step: which lane, its block, whether it opens or closes the lane's item
-  struct Step {
-    int lane, b;
-    bool first_blk, last_blk;
-    uint32_t g, n, s;   // global step, lane's item counter, lane's step counter
-  };
-  SB_DEVICE bool next(Step& st) {
-    int L = turn;
-    if (!lane_has_work(L)) {
-      L ^= 1;
-      if (!lane_has_work(L)) return false;
-    }
-    turn = L ^ 1;
-    int blk = L ? blk1 : blk0;
-    int nb = L ? nb1 : nb0;
-    if (blk < 0) {   // open the lane's next item
-      const int it = first + (L ? k1 : k0) * stride;
-      nb = tc_geom<G>(it, hkv, items, qs, ql, past).n_blocks;
-      blk = 0;
-      if (L) cur1 = it, nb1 = nb, k1 += 2, ++n1;
-      else cur0 = it, nb0 = nb, k0 += 2, ++n0;
-    }
-    st.lane = L;
-    st.b = blk;
-    st.first_blk = blk == 0;
-    st.last_blk = blk == nb - 1;
-    st.g = g++;
-    st.n = (L ? n1 : n0) - 1;
-    st.s = L ? s1 : s0;
-    if (L) ++s1, blk1 = st.last_blk ? -1 : blk + 1;
-    else ++s0, blk0 = st.last_blk ? -1 : blk + 1;
-    return true;
-  }
-};
-
 template <int G>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, head, token) over qkv
@@ -182,15 +106,16 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
                        int n_items_total, const int32_t* __restrict__ seq_q_start,
                        const int32_t* __restrict__ seq_q_len, const int32_t* __restrict__ seq_past,
                        int hq, int hkv, int layer, float scale_log2) {
+  constexpr int QT = 128 / G;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const uint32_t s_q = smem_u32(smem);                       // Q of lane 0 | lane 1: 2 x 32 KiB
-  const uint32_t s_k = s_q + 2 * kTileBytes2;                // K ring, 2 x 32 KiB
-  const uint32_t s_v = s_k + 2 * kTileBytes2;                // V ring, 2 x 32 KiB
-  const uint32_t s_p = s_v + 2 * kTileBytes2;                // P (shared by the lanes), 32 KiB
+  const uint32_t s_q = smem_u32(smem);                       // 2 x 32 KiB
+  const uint32_t s_k = s_q + 2 * kTileBytes2;                // 2 x 32 KiB
+  const uint32_t s_v = s_k + 2 * kTileBytes2;                // 2 x 32 KiB
+  const uint32_t s_p = s_v + 2 * kTileBytes2;                // 32 KiB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTileBytes2);
-  // barrier indices: [2] = per lane for Q / S / O, per ring stage for K / V
+  // barrier indices
   enum { Q_FULL = 0, Q_EMPTY = 2, K_FULL = 4, K_EMPTY = 6, V_FULL = 8, V_EMPTY = 10, S_FULL = 12,
          S_EMPTY = 14, P_FULL = 16, P_EMPTY = 17, O_FULL = 18, O_EMPTY = 20, N_BARS = 22 };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + N_BARS);
@@ -198,18 +123,17 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int kProducerWarp = 8, kMmaWarp = 9;
 
-  if (warp == kProducerWarp && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_kv);
     tma_prefetch_desc(&tm_pre);
   }
-  if (warp == kMmaWarp && lane == 0) {
+  if (warp == 5 && lane == 0) {
     for (int i = 0; i < N_BARS; ++i) {
       const bool from_softmax = (i >= S_EMPTY && i < S_EMPTY + 2) || i == P_FULL ||
                                 (i >= O_EMPTY && i < O_EMPTY + 2);
-      mbar_init(bar(i), from_softmax ? 4 : 1);  // softmax side: one arrival per warp of a lane
+      mbar_init(bar(i), from_softmax ? 4 : 1);  // softmax side: one arrival per warp
     }
     fence_mbar_init();
   }
@@ -221,288 +145,310 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;        // S of lane L at columns L*128
-  const uint32_t tmem_o = tmem_base + 256;  // O of lane L at columns 256 + L*128
+  const uint32_t tmem_s = tmem_base;        // S[sb] at columns sb*128
+  const uint32_t tmem_o = tmem_base + 256;  // O[ob] at columns 256 + ob*128
 
-  TcWalk<G> walk;
-  walk.init(items, seq_q_start, seq_q_len, seq_past, hkv, blockIdx.x, gridDim.x, n_items_total);
-  typename TcWalk<G>::Step st;
-
-  if (warp == kProducerWarp) {
-    // ===================== TMA producer =====================
+  if (warp == 4 || warp == 6) {
+    // ===================== TMA producers =====================
+    // warp 4 streams Q tiles and K blocks, warp 6 the V blocks.  Two independent flows: a V
+    // stage frees up only when its P.V has retired (after the softmax), a K stage as soon as
+    // its S = Q.K^T has — one in-order producer would hold the next K block (and with it the
+    // next S) hostage behind the wait for the previous block's V stage.
+    const bool v_flow = warp == 6;
     if (lane == 0) {
-      while (walk.next(st)) {
-        const int L = st.lane;
-        const TcGeom ge = walk.geom(L);
-        if (st.first_blk) {   // the lane's Q tile: free once the last S of its previous item retired
-          mbar_wait(bar(Q_EMPTY + L), (st.n & 1) ^ 1);
-          mbar_arrive_expect_tx(bar(Q_FULL + L), kTileBytes2);
-          const uint32_t qd = s_q + L * kTileBytes2;
-          tma_load_3d(qd, &tm_q, bar(Q_FULL + L), 0, ge.kvh * G, ge.q_start + ge.qt0);
-          tma_load_3d(qd + kHalfBytes, &tm_q, bar(Q_FULL + L), 64, ge.kvh * G,
+      uint32_t g = 0;  // global block counter of this CTA
+      uint32_t n = 0;  // item counter of this CTA
+      for (int item = blockIdx.x; item < n_items_total; item += gridDim.x, ++n) {
+        const TcGeom ge = tc_geom<G>(item, hkv, items, seq_q_start, seq_q_len, seq_past);
+        if (!v_flow) {
+          const uint32_t qb = n & 1;
+          mbar_wait(bar(Q_EMPTY + qb), ((n >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar(Q_FULL + qb), kTileBytes2);
+          const uint32_t qd = s_q + qb * kTileBytes2;
+          tma_load_3d(qd, &tm_q, bar(Q_FULL + qb), 0, ge.kvh * G, ge.q_start + ge.qt0);
+          tma_load_3d(qd + kHalfBytes, &tm_q, bar(Q_FULL + qb), 64, ge.kvh * G,
                       ge.q_start + ge.qt0);
         }
-        bool is_pre;
-        int j0, n16;
-        tc_block<G>(ge, st.b, is_pre, j0, n16);
-        const int n32 = (n16 + kBoxRows - 1) / kBoxRows;
-        const uint32_t rs = st.g & 1, ph = ((st.g >> 1) & 1) ^ 1;
-        const int kcol = is_pre ? ge.kvh * kHeadDim : (hq + ge.kvh) * kHeadDim;
-        const int vcol = kcol + hkv * kHeadDim;
-        const int row0 = is_pre ? j0 : ge.q_start + j0;
-        mbar_wait(bar(K_EMPTY + rs), ph);
-        mbar_arrive_expect_tx(bar(K_FULL + rs), n32 * 2 * kBoxBytes);
-        for (int i = 0; i < n32; ++i) {
+        for (int b = 0; b < ge.n_blocks; ++b, ++g) {
+          bool is_pre;
+          int j0, n16;
+          tc_block<G>(ge, b, is_pre, j0, n16);
+          const int n32 = (n16 + kBoxRows - 1) / kBoxRows;
+          const uint32_t st = g & 1, ph = ((g >> 1) & 1) ^ 1;
+          const int kcol = is_pre ? ge.kvh * kHeadDim : (hq + ge.kvh) * kHeadDim;
+          const int col = v_flow ? kcol + hkv * kHeadDim : kcol;
+          const int row0 = is_pre ? j0 : ge.q_start + j0;
+          const uint32_t full = bar((v_flow ? V_FULL : K_FULL) + st);
+          const uint32_t base = (v_flow ? s_v : s_k) + st * kTileBytes2;
+          mbar_wait(bar((v_flow ? V_EMPTY : K_EMPTY) + st), ph);
+          mbar_arrive_expect_tx(full, n32 * 2 * kBoxBytes);
+          for (int i = 0; i < n32; ++i) {
 #pragma unroll
-          for (int dh = 0; dh < 2; ++dh) {
-            const uint32_t dst = s_k + rs * kTileBytes2 + dh * kHalfBytes + i * kBoxBytes;
-            if (is_pre)
-              tma_load_3d(dst, &tm_pre, bar(K_FULL + rs), kcol + dh * 64, row0 + i * kBoxRows, layer);
-            else
-              tma_load_2d(dst, &tm_kv, bar(K_FULL + rs), kcol + dh * 64, row0 + i * kBoxRows);
-          }
-        }
-        mbar_wait(bar(V_EMPTY + rs), ph);
-        mbar_arrive_expect_tx(bar(V_FULL + rs), n32 * 2 * kBoxBytes);
-        for (int i = 0; i < n32; ++i) {
-#pragma unroll
-          for (int dh = 0; dh < 2; ++dh) {
-            const uint32_t dst = s_v + rs * kTileBytes2 + dh * kHalfBytes + i * kBoxBytes;
-            if (is_pre)
-              tma_load_3d(dst, &tm_pre, bar(V_FULL + rs), vcol + dh * 64, row0 + i * kBoxRows, layer);
-            else
-              tma_load_2d(dst, &tm_kv, bar(V_FULL + rs), vcol + dh * 64, row0 + i * kBoxRows);
-          }
-        }
-      }
-    }
-  } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    // issue order: S(g+1) before P.V(g), so that the tensor pipe computes the next step's
-    // scores (the other lane's, normally) while this step's softmax is still running
-    bool have_pending = false;
-    uint32_t p_g = 0, p_n16 = 0, p_lane = 0, p_n = 0;
-    bool p_first = false, p_last = false;
-    auto do_pv = [&]() {
-      mbar_wait(bar(P_FULL), p_g & 1);
-      mbar_wait(bar(V_FULL + (p_g & 1)), (p_g >> 1) & 1);
-      if (p_first) mbar_wait(bar(O_EMPTY + p_lane), (p_n & 1) ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t rs = p_g & 1;
-        const uint32_t d = tmem_o + p_lane * 128;
-        const uint32_t idesc = umma_idesc_bf16(128, 128) | kUmmaBMajorMN;
-        const int ksteps = static_cast<int>(p_n16) >> 4;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t adesc = umma_desc_k_sw128(s_p + (kk >> 2) * kHalfBytes) + 2 * (kk & 3);
-          const uint64_t bdesc =
-              umma_desc_mn_sw128(s_v + rs * kTileBytes2 + kk * 2048, kHalfBytes, 1024);
-          tc_mma_f16(d, adesc, bdesc, idesc, (p_first && kk == 0) ? 0u : 1u);
-        }
-        tc_commit(bar(V_EMPTY + rs));
-        tc_commit(bar(P_EMPTY));
-        if (p_last) tc_commit(bar(O_FULL + p_lane));
-      }
-      __syncwarp();
-    };
-    while (walk.next(st)) {
-      const int L = st.lane;
-      const TcGeom ge = walk.geom(L);
-      bool is_pre;
-      int j0, n16;
-      tc_block<G>(ge, st.b, is_pre, j0, n16);
-      const uint32_t rs = st.g & 1;
-      if (st.first_blk) mbar_wait(bar(Q_FULL + L), st.n & 1);
-      mbar_wait(bar(K_FULL + rs), (st.g >> 1) & 1);
-      mbar_wait(bar(S_EMPTY + L), (st.s & 1) ^ 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t idesc = umma_idesc_bf16(128, n16);
-        const uint32_t d = tmem_s + L * 128;
-#pragma unroll
-        for (int dh = 0; dh < 2; ++dh) {
-          const uint64_t adesc = umma_desc_k_sw128(s_q + L * kTileBytes2 + dh * kHalfBytes);
-          const uint64_t bdesc = umma_desc_k_sw128(s_k + rs * kTileBytes2 + dh * kHalfBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (dh | k) != 0 ? 1u : 0u);
-        }
-        tc_commit(bar(S_FULL + L));
-        tc_commit(bar(K_EMPTY + rs));
-        if (st.last_blk) tc_commit(bar(Q_EMPTY + L));
-      }
-      __syncwarp();
-      if (have_pending) do_pv();
-      have_pending = true;
-      p_g = st.g;
-      p_n16 = static_cast<uint32_t>(n16);
-      p_lane = static_cast<uint32_t>(L);
-      p_n = st.n;
-      p_first = st.first_blk;
-      p_last = st.last_blk;
-    }
-    if (have_pending) do_pv();
-  } else {
-    // ===================== softmax / correction / epilogue: lane = warp / 4 =====================
-    const int my = warp >> 2;
-    const int r = (warp & 3) * 32 + lane;  // tile row == TMEM lane
-    const int t_in = r / G;                // token within the q tile
-    const int h_in = r - t_in * G;         // query head within the GQA group
-    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t p_row = s_p + r * 128;
-    const int sw = r & 7;
-    const uint32_t s_addr = tmem_s + my * 128 + lane_sel;
-    const uint32_t o_addr = tmem_o + my * 128 + lane_sel;
-    float m_used = 0.f, l_run = 0.f;
-    while (walk.next(st)) {
-      if (st.lane != my) continue;
-      const TcGeom ge = walk.geom(my);
-      const int q_own = ge.qt0 + t_in;    // index of this row's token among the own tokens
-      bool is_pre;
-      int j0, n16;
-      tc_block<G>(ge, st.b, is_pre, j0, n16);
-      // columns c of this block are valid for this row iff c < vlim
-      const int vlim = min(is_pre ? ge.past - j0 : q_own - j0 + 1, n16);
-      const int n_chunks = (n16 + 31) >> 5;
-      mbar_wait(bar(S_FULL + my), st.s & 1);
-      tc_fence_after();
-      // One softmax warp per lane and SM sub-partition: little hides ALU latency but ILP, and
-      // every instruction counts.  So (a) chunks that are valid for every row of the warp (all
-      // but the diagonal one: lane 0 holds the warp's smallest limit, limits grow with the
-      // lane) take a path without per-element predicates, (b) max and sum run on four
-      // independent accumulators, (c) exp2 is the bare MUFU (ex2.approx.ftz).  TMEM reads are
-      // cheap (tens of cycles), so the row is read twice, 32 columns at a time, instead of
-      // holding 128 scores in registers.
-      const int vmin = __shfl_sync(0xffffffffu, vlim, 0);
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + c * 32, v);
-        tmem_ld_wait();
-        if (c * 32 + 32 <= vmin) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < vlim) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
-        }
-      }
-      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      mx *= scale_log2;  // scale > 0: max commutes with the scaling
-      // ---- running max with lazy rescale ----
-      float alpha = 1.f;
-      bool need = false;
-      if (st.first_blk) {
-        m_used = (mx == -INFINITY) ? 0.f : mx;
-        l_run = 0.f;
-      } else if (mx > m_used + kRescaleThreshold) {
-        alpha = ex2_approx(m_used - mx);
-        m_used = mx;
-        l_run *= alpha;
-        need = true;
-      }
-      // the previous step's P.V (either lane's) must have retired before P is overwritten; it
-      // also orders this lane's O behind its own previous P.V for the rescale
-      mbar_wait(bar(P_EMPTY), (st.g & 1) ^ 1);
-      if (__any_sync(0xffffffffu, need)) {
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32(o_addr + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32(o_addr + c * 32, o);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-      }
-      // ---- P = exp2(s*scale - m) -> bf16 -> shared memory (K-major, SW128) ----
-      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
-      const float neg_m = -m_used;
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_addr + c * 32, v);
-        tmem_ld_wait();
-        if (c == n_chunks - 1) {   // the scores have left TMEM: S may take the lane's next block
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(S_EMPTY + my));
-        }
-        if (c * 32 + 32 <= vmin) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {   // packed pairs overwrite the scores in place
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2, neg_m));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, neg_m));
-            ps4[i & 3] += p0 + p1;
-            v[i] = pack_bf16x2(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c0 = c * 32 + 2 * i;
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2, neg_m));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, neg_m));
-            p0 = c0 < vlim ? p0 : 0.f;
-            p1 = c0 + 1 < vlim ? p1 : 0.f;
-            ps4[i & 3] += p0 + p1;
-            v[i] = pack_bf16x2(p0, p1);
-          }
-        }
-        // 32 columns = 64 B = four 16-byte chunks of k-block (c >> 1)
-        const uint32_t base = p_row + (c >> 1) * kHalfBytes;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int cc = (c & 1) * 4 + q4;
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((cc ^ sw) << 4)),
-                       "r"(v[4 * q4]), "r"(v[4 * q4 + 1]), "r"(v[4 * q4 + 2]), "r"(v[4 * q4 + 3])
-                       : "memory");
-        }
-      }
-      l_run += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(P_FULL));
-      if (st.last_blk) {
-        // ---- epilogue: O / l -> global (the other lane keeps the tensor core busy meanwhile) ----
-        mbar_wait(bar(O_FULL + my), st.n & 1);
-        tc_fence_after();
-        const float inv = 1.0f / l_run;
-        const bool row_ok = q_own < ge.q_len;
-        __nv_bfloat16* dst = out + static_cast<size_t>(ge.q_start + q_own) * (hq * kHeadDim) +
-                             (ge.kvh * G + h_in) * kHeadDim;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {   // two 64-column halves: 64 live registers
-          uint32_t o[2][32];
-          tmem_ld_32x32(o_addr + half * 64, o[0]);
-          tmem_ld_32x32(o_addr + half * 64 + 32, o[1]);
-          tmem_ld_wait();
-          if (half == 1) {  // the accumulator has left TMEM: hand O back before the stores
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(O_EMPTY + my));
-          }
-          if (row_ok) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t pk[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                pk[i] = pack_bf16x2(__uint_as_float(o[c][2 * i]) * inv,
-                                    __uint_as_float(o[c][2 * i + 1]) * inv);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                st_v4(dst + half * 64 + c * 32 + 8 * i,
-                      make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]));
+            for (int dh = 0; dh < 2; ++dh) {
+              const uint32_t dst = base + dh * kHalfBytes + i * kBoxBytes;
+              if (is_pre)
+                tma_load_3d(dst, &tm_pre, full, col + dh * 64, row0 + i * kBoxRows, layer);
+              else
+                tma_load_2d(dst, &tm_kv, full, col + dh * 64, row0 + i * kBoxRows);
             }
           }
         }
       }
     }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    uint32_t g = 0, n = 0;
+    bool have_pending = false;
+    uint32_t p_g = 0, p_n16 = 0, p_ob = 0, p_opar = 0;
+    bool p_first = false, p_last = false;
+
+    auto do_pv = [&]() {
+      mbar_wait(bar(P_FULL), p_g & 1);
+      mbar_wait(bar(V_FULL + (p_g & 1)), (p_g >> 1) & 1);
+      if (p_first) mbar_wait(bar(O_EMPTY + p_ob), p_opar ^ 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = p_g & 1;
+        const uint32_t d = tmem_o + p_ob * 128;
+        const uint32_t idesc = umma_idesc_bf16(128, 128) | kUmmaBMajorMN;
+        const int ksteps = static_cast<int>(p_n16) >> 4;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t adesc = umma_desc_k_sw128(s_p + (kk >> 2) * kHalfBytes) + 2 * (kk & 3);
+          const uint64_t bdesc =
+              umma_desc_mn_sw128(s_v + st * kTileBytes2 + kk * 2048, kHalfBytes, 1024);
+          tc_mma_f16(d, adesc, bdesc, idesc, (p_first && kk == 0) ? 0u : 1u);
+        }
+        tc_commit(bar(V_EMPTY + st));
+        tc_commit(bar(P_EMPTY));
+        if (p_last) tc_commit(bar(O_FULL + p_ob));
+      }
+      __syncwarp();
+    };
+
+    for (int item = blockIdx.x; item < n_items_total; item += gridDim.x, ++n) {
+      const TcGeom ge = tc_geom<G>(item, hkv, items, seq_q_start, seq_q_len, seq_past);
+      const uint32_t qb = n & 1;
+      mbar_wait(bar(Q_FULL + qb), (n >> 1) & 1);
+      for (int b = 0; b < ge.n_blocks; ++b, ++g) {
+        bool is_pre;
+        int j0, n16;
+        tc_block<G>(ge, b, is_pre, j0, n16);
+        const uint32_t st = g & 1;
+        mbar_wait(bar(K_FULL + st), (g >> 1) & 1);
+        mbar_wait(bar(S_EMPTY + st), ((g >> 1) & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t idesc = umma_idesc_bf16(128, n16);
+          const uint32_t d = tmem_s + st * 128;
+#pragma unroll
+          for (int dh = 0; dh < 2; ++dh) {
+            const uint64_t adesc = umma_desc_k_sw128(s_q + qb * kTileBytes2 + dh * kHalfBytes);
+            const uint64_t bdesc = umma_desc_k_sw128(s_k + st * kTileBytes2 + dh * kHalfBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (dh | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(bar(S_FULL + st));
+          tc_commit(bar(K_EMPTY + st));
+          if (b == ge.n_blocks - 1) tc_commit(bar(Q_EMPTY + qb));
+        }
+        __syncwarp();
+        if (have_pending) do_pv();
+        have_pending = true;
+        p_g = g;
+        p_n16 = static_cast<uint32_t>(n16);
+        p_ob = n & 1;
+        p_opar = (n >> 1) & 1;
+        p_first = b == 0;
+        p_last = b == ge.n_blocks - 1;
+      }
+    }
+    if (have_pending) do_pv();
+  } else {
+    // ===================== softmax / correction / epilogue (warps 0-3) =====================
+    const int r = warp * 32 + lane;       // tile row == TMEM lane
+    const int t_in = r / G;               // token within the q tile
+    const int h_in = r - t_in * G;        // query head within the GQA group
+    const uint32_t lane_sel = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t p_row = s_p + r * 128;
+    const int sw = r & 7;
+    uint32_t g = 0, n = 0;
+    float m_used = 0.f, l_run = 0.f;
+    // The epilogue of an item is deferred until the first block of the NEXT item has been
+    // handed to the tensor core: the wait for the last P.V (O_FULL) then overlaps useful work
+    // instead of idling the softmax warps once per item (O is double-buffered).
+    bool ep_pending = false;
+    uint32_t ep_ob = 0, ep_par = 0;
+    float ep_inv = 0.f;
+    bool ep_row_ok = false;
+    __nv_bfloat16* ep_dst = nullptr;
+    auto flush_epilogue = [&]() {
+      if (!ep_pending) return;
+      ep_pending = false;
+      mbar_wait(bar(O_FULL + ep_ob), ep_par);
+      tc_fence_after();
+      const uint32_t o_addr = tmem_o + ep_ob * 128 + lane_sel;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {   // two 64-column halves: 64 live registers
+        uint32_t v[2][32];
+        tmem_ld_32x32(o_addr + half * 64, v[0]);
+        tmem_ld_32x32(o_addr + half * 64 + 32, v[1]);
+        tmem_ld_wait();
+        if (half == 1) {  // the accumulator has left TMEM: hand O[ob] back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(O_EMPTY + ep_ob));
+        }
+        if (ep_row_ok) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              o[i] = pack_bf16x2(__uint_as_float(v[c][2 * i]) * ep_inv,
+                                 __uint_as_float(v[c][2 * i + 1]) * ep_inv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              st_v4(ep_dst + half * 64 + c * 32 + 8 * i,
+                    make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+          }
+        }
+      }
+    };
+    for (int item = blockIdx.x; item < n_items_total; item += gridDim.x, ++n) {
+      const TcGeom ge = tc_geom<G>(item, hkv, items, seq_q_start, seq_q_len, seq_past);
+      const int q_own = ge.qt0 + t_in;    // index of this row's token among the own tokens
+      const uint32_t ob = n & 1;
+      for (int b = 0; b < ge.n_blocks; ++b, ++g) {
+        bool is_pre;
+        int j0, n16;
+        tc_block<G>(ge, b, is_pre, j0, n16);
+        // columns c of this block are valid for this row iff c < vlim
+        const int vlim = min(is_pre ? ge.past - j0 : q_own - j0 + 1, n16);
+        const uint32_t sb = g & 1;
+        const int n_chunks = (n16 + 31) >> 5;
+        mbar_wait(bar(S_FULL + sb), (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t s_addr = tmem_s + sb * 128 + lane_sel;
+        // ---- the whole score row into registers (one TMEM round trip), S[sb] released ----
+        uint32_t v[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < n_chunks) tmem_ld_32x32(s_addr + c * 32, v[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
+        // One softmax warp per SM sub-partition: nothing hides ALU latency but ILP, and every
+        // instruction counts.  So (a) chunks that are valid for every row of the warp (all but
+        // the diagonal one: lane 0 holds the warp's smallest limit, limits grow with the lane)
+        // take a path without per-element predicates, (b) max and sum run on four independent
+        // accumulators, (c) exp2 is the bare MUFU (ex2.approx.ftz).
+        const int vmin = __shfl_sync(0xffffffffu, vlim, 0);
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < n_chunks) {
+            if (c * 32 + 32 <= vmin) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < vlim) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
+            }
+          }
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        mx *= scale_log2;  // scale > 0: max commutes with the scaling
+        // ---- running max with lazy rescale ----
+        float alpha = 1.f;
+        bool need = false;
+        if (b == 0) {
+          m_used = (mx == -INFINITY) ? 0.f : mx;
+          l_run = 0.f;
+        } else if (mx > m_used + kRescaleThreshold) {
+          alpha = ex2_approx(m_used - mx);
+          m_used = mx;
+          l_run *= alpha;
+          need = true;
+        }
+        // ---- P = exp2(s*scale - m) -> bf16 (registers) ----
+        float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float neg_m = -m_used;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < n_chunks) {
+            if (c * 32 + 32 <= vmin) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {   // packed pairs overwrite the scores in place
+                const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), scale_log2, neg_m));
+                const float p1 =
+                    ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2, neg_m));
+                ps4[i & 3] += p0 + p1;
+                v[c][i] = pack_bf16x2(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int c0 = c * 32 + 2 * i;
+                float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i]), scale_log2, neg_m));
+                float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * i + 1]), scale_log2, neg_m));
+                p0 = c0 < vlim ? p0 : 0.f;
+                p1 = c0 + 1 < vlim ? p1 : 0.f;
+                ps4[i & 3] += p0 + p1;
+                v[c][i] = pack_bf16x2(p0, p1);
+              }
+            }
+          }
+        const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+        l_run += psum;
+        // the previous block's PV must have retired before O is rescaled or P is overwritten
+        mbar_wait(bar(P_EMPTY), (g & 1) ^ 1);
+        if (__any_sync(0xffffffffu, need)) {
+          tc_fence_after();
+          const uint32_t o_addr = tmem_o + ob * 128 + lane_sel;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(o_addr + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(o_addr + c * 32, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        // ---- P -> shared memory (K-major, SW128): 32 columns = four 16-byte chunks ----
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < n_chunks) {
+            const uint32_t base = p_row + (c >> 1) * kHalfBytes;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int cc = (c & 1) * 4 + q4;
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + ((cc ^ sw) << 4)),
+                           "r"(v[c][4 * q4]), "r"(v[c][4 * q4 + 1]), "r"(v[c][4 * q4 + 2]),
+                           "r"(v[c][4 * q4 + 3])
+                           : "memory");
+            }
+          }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(P_FULL));
+        flush_epilogue();   // the previous item's, if any: the tensor core is busy with this block
+        if (b == ge.n_blocks - 1) {
+          ep_pending = true;
+          ep_ob = ob;
+          ep_par = (n >> 1) & 1;
+          ep_inv = 1.0f / l_run;
+          ep_row_ok = q_own < ge.q_len;
+          ep_dst = out + static_cast<size_t>(ge.q_start + q_own) * (hq * kHeadDim) +
+                   (ge.kvh * G + h_in) * kHeadDim;
+        }
+      }
+    }
+    flush_epilogue();
   }
 
   tc_fence_before();
