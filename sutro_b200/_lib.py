@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsutro_b200.so")
+# SB200_LIB: load another build of the same library (tools/build_trace_lib.sh's instrumented twin)
+LIB_PATH = os.environ.get("SB200_LIB") or os.path.join(_HERE, "libsutro_b200.so")
 
 _lib = None
 

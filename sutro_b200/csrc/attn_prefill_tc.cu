@@ -91,6 +91,23 @@ SB_DEVICE void tc_block(const TcGeom& g, int b, bool& is_pre, int& j0, int& n16)
   n16 = (limit + 15) & ~15;
 }
 
+#ifdef SB200_ATTN_TRACE
+// Debug build only (tools/build_trace_lib.sh): CTA `g_tr_cta` stamps %clock at its pipeline
+// hand-offs, kTrCap stamps per role, for `tools/attn_bench.py --trace`.  The pointer lives in
+// the constant bank, so a stamp costs a compare, a CS2R and a store.  The product library is
+// compiled without the macro and carries none of it.
+constexpr int kTrCap = 1024;
+__constant__ long long* g_tr = nullptr;
+__constant__ int g_tr_cta = 0;
+#define TR(role, idx)                                                                   \
+  do {                                                                                  \
+    if (g_tr != nullptr && static_cast<int>(blockIdx.x) == g_tr_cta && (idx) < kTrCap)  \
+      g_tr[(role) * kTrCap + (idx)] = static_cast<long long>(clock());                 \
+  } while (0)
+#else
+#define TR(role, idx) do { } while (0)
+#endif
+
 SB_DEVICE float ex2_approx(float x) {   // MUFU.EX2: 2^x, flushes denormals (x <= -126 -> 0)
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -181,6 +198,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
           const uint32_t full = bar((v_flow ? V_FULL : K_FULL) + st);
           const uint32_t base = (v_flow ? s_v : s_k) + st * kTileBytes2;
           mbar_wait(bar((v_flow ? V_EMPTY : K_EMPTY) + st), ph);
+          TR(v_flow ? 1 : 0, 2 * g);
           mbar_arrive_expect_tx(full, n32 * 2 * kBoxBytes);
           for (int i = 0; i < n32; ++i) {
 #pragma unroll
@@ -192,6 +210,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
                 tma_load_2d(dst, &tm_kv, full, col + dh * 64, row0 + i * kBoxRows);
             }
           }
+          TR(v_flow ? 1 : 0, 2 * g + 1);
         }
       }
     }
@@ -203,9 +222,13 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
     bool p_first = false, p_last = false;
 
     auto do_pv = [&]() {
+      if (lane == 0) TR(3, 4 * p_g);
       mbar_wait(bar(P_FULL), p_g & 1);
+      if (lane == 0) TR(3, 4 * p_g + 1);
       mbar_wait(bar(V_FULL + (p_g & 1)), (p_g >> 1) & 1);
+      if (lane == 0) TR(3, 4 * p_g + 2);
       if (p_first) mbar_wait(bar(O_EMPTY + p_ob), p_opar ^ 1);
+      if (lane == 0) TR(3, 4 * p_g + 3);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t st = p_g & 1;
@@ -234,8 +257,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
         int j0, n16;
         tc_block<G>(ge, b, is_pre, j0, n16);
         const uint32_t st = g & 1;
+        if (lane == 0) TR(2, 4 * g);
+        if (b == 0 && lane == 0) TR(2, 4 * g + 3);
         mbar_wait(bar(K_FULL + st), (g >> 1) & 1);
+        if (lane == 0) TR(2, 4 * g + 1);
         mbar_wait(bar(S_EMPTY + st), ((g >> 1) & 1) ^ 1);
+        if (lane == 0) TR(2, 4 * g + 2);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t idesc = umma_idesc_bf16(128, n16);
@@ -327,7 +354,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
         const int vlim = min(is_pre ? ge.past - j0 : q_own - j0 + 1, n16);
         const uint32_t sb = g & 1;
         const int n_chunks = (n16 + 31) >> 5;
+        if (threadIdx.x == 0) TR(4, 8 * g);
         mbar_wait(bar(S_FULL + sb), (g >> 1) & 1);
+        if (threadIdx.x == 0) TR(4, 8 * g + 1);
         tc_fence_after();
         const uint32_t s_addr = tmem_s + sb * 128 + lane_sel;
         // ---- the whole score row into registers (one TMEM round trip), S[sb] released ----
@@ -339,6 +368,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(S_EMPTY + sb));
+        if (threadIdx.x == 0) TR(4, 8 * g + 2);
         // One softmax warp per SM sub-partition: nothing hides ALU latency but ILP, and every
         // instruction counts.  So (a) chunks that are valid for every row of the warp (all but
         // the diagonal one: lane 0 holds the warp's smallest limit, limits grow with the lane)
@@ -360,6 +390,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
           }
         float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         mx *= scale_log2;  // scale > 0: max commutes with the scaling
+        if (threadIdx.x == 0) TR(5, 4 * g);
         // ---- running max with lazy rescale ----
         float alpha = 1.f;
         bool need = false;
@@ -375,6 +406,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
         // ---- P = exp2(s*scale - m) -> bf16 (registers) ----
         float ps4[4] = {0.f, 0.f, 0.f, 0.f};
         const float neg_m = -m_used;
+        if (threadIdx.x == 0) TR(5, 4 * g + 1);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c < n_chunks) {
@@ -403,7 +435,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
         const float psum = (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
         l_run += psum;
         // the previous block's PV must have retired before O is rescaled or P is overwritten
+        if (threadIdx.x == 0) TR(4, 8 * g + 3);
         mbar_wait(bar(P_EMPTY), (g & 1) ^ 1);
+        if (threadIdx.x == 0) TR(4, 8 * g + 4);
         if (__any_sync(0xffffffffu, need)) {
           tc_fence_after();
           const uint32_t o_addr = tmem_o + ob * 128 + lane_sel;
@@ -436,7 +470,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tm_q,    // 3-D (d, h
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(P_FULL));
-        flush_epilogue();   // the previous item's, if any: the tensor core is busy with this block
+        if (threadIdx.x == 0) TR(4, 8 * g + 5);
+        flush_epilogue();
+        if (threadIdx.x == 0) TR(4, 8 * g + 6);   // the previous item's, if any: the tensor core is busy with this block
         if (b == ge.n_blocks - 1) {
           ep_pending = true;
           ep_ob = ob;
@@ -582,3 +618,11 @@ int attn_prefill_dense(const void* qkv, int t_rows, void* out, const void* prefi
 }
 
 }  // namespace sb
+
+#ifdef SB200_ATTN_TRACE
+extern "C" int sb200_attn_trace(long long* dev_buf, int cta) {
+  if (cudaMemcpyToSymbol(sb::g_tr, &dev_buf, sizeof(dev_buf)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(sb::g_tr_cta, &cta, sizeof(cta)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif

@@ -25,6 +25,10 @@ ap.add_argument("--tokens", type=int, default=32768)
 ap.add_argument("--hq", type=int, default=32)
 ap.add_argument("--hkv", type=int, default=8)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--trace", type=int, default=-1, help="CTA whose pipeline timeline to print "
+                "(needs SB200_LIB=tools/_trace/libsutro_b200_trace.so)")
+ap.add_argument("--trace-from", type=int, default=40)
+ap.add_argument("--trace-n", type=int, default=12)
 a = ap.parse_args()
 dev = "cuda"
 hq, hkv = a.hq, a.hkv
@@ -105,6 +109,37 @@ def timeit(fn):
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / a.iters
 
+
+if a.trace >= 0:
+    import ctypes as C
+    CAP = 1024
+    buf = torch.zeros(6 * CAP, dtype=torch.int64, device=dev)
+    fn = L.lib().sb200_attn_trace
+    fn.argtypes, fn.restype = [C.c_void_p, C.c_int], C.c_int
+    for _ in range(3):
+        run_tc()
+    torch.cuda.synchronize()
+    assert fn(L.ptr(buf), a.trace) == 0
+    run_tc()
+    torch.cuda.synchronize()
+    fn(None, 0)
+    tr = buf.cpu().view(6, CAP).tolist()   # 32-bit %clock stamps: fine within one launch
+    g0 = a.trace_from
+    t0 = tr[2][4 * g0]
+    rel = lambda x: "     ." if x == 0 else f"{x - t0:6d}"
+    print("cycles relative to the MMA warp reaching block", g0, "(CTA", a.trace, ")")
+    print("  g | K: slot  issued | V: slot  issued | S-MMA: at   kfull  issue | PV: at   pfull  vfull  issue |"
+          " softmax: at  sfull  ld'd   math  pfree  p-out  epi | max'd  alpha")
+    for g in range(g0, g0 + a.trace_n):
+        k, v, m, pv, sm = (tr[0][2 * g:2 * g + 2], tr[1][2 * g:2 * g + 2], tr[2][4 * g:4 * g + 3],
+                           tr[3][4 * g:4 * g + 4], tr[4][8 * g:8 * g + 7])
+        new = "*" if tr[2][4 * g + 3] else " "
+        print(f"{g:3d}{new}| {rel(k[0])} {rel(k[1])} | {rel(v[0])} {rel(v[1])} | {rel(m[0])} {rel(m[1])} {rel(m[2])} |"
+              f" {rel(pv[0])} {rel(pv[1])} {rel(pv[2])} {rel(pv[3])} | " + " ".join(rel(x) for x in sm) +
+              " | " + " ".join(rel(x) for x in tr[5][4 * g:4 * g + 2]))
+    last = max(i for i in range(CAP // 8) if tr[4][8 * i + 5])
+    print("blocks:", last + 1, " cycles per block:", (tr[4][8 * last + 5] - tr[4][5]) // max(last, 1))
+    sys.exit(0)
 
 t_tc, t_v1 = timeit(run_tc), timeit(run_v1)
 diff = (out.float() - out2.float()).abs().max().item()
