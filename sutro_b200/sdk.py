@@ -113,8 +113,12 @@ class Sutro(Templates, BaseSutroClient):
     def __init__(self, devices: Optional[List[int]] = None, weights_seed: int = 0,
                  engine_options: Optional[Dict[str, Any]] = None, cache_dir: Optional[str] = None,
                  verbose: bool = True, on_progress=None,
-                 model_paths: Optional[Dict[str, str]] = None):
+                 model_paths: Optional[Dict[str, str]] = None, fsm_limits=None):
         self.devices = devices or [0]
+        # schema_fsm.FsmLimits: bounds for what a JSON schema leaves open (strings without
+        # maxLength stop at 64 characters, arrays without maxItems at 8 items, ... by default —
+        # the hosted service has no such caps; raise them here when outputs need the room)
+        self.fsm_limits = fsm_limits
         # model name -> Hugging Face model directory (config.json, tokenizer.json, *.safetensors);
         # models without a path run on seeded random weights and the synthetic vocabulary
         self.model_paths = dict(model_paths or {})
@@ -162,18 +166,18 @@ class Sutro(Templates, BaseSutroClient):
         return self._engines[model]
 
     @staticmethod
-    def _default_max_new_tokens(eng, json_schema, thinking_chars=None) -> int:
+    def _default_max_new_tokens(eng, json_schema, thinking_chars=None, limits=None) -> int:
         """Output budget when sampling_params names none.  Schema jobs: the longest string the
         schema's automaton accepts (every token is at least one byte), so a constrained row
         can always close its object — a row cut mid-object would not be JSON.  Free text: 512."""
         spec = getattr(eng, "spec", None)
         cap = max(16, getattr(spec, "max_position", 4096) // 2)
         if thinking_chars is not None and hasattr(eng, "compile_schema"):
-            longest = eng.compile_schema(json_schema, None, int(thinking_chars)).longest_path()
+            longest = eng.compile_schema(json_schema, limits, int(thinking_chars)).longest_path()
             return int(min(max(longest, 8), cap)) if longest is not None else \
                 int(min(512 + 4 * int(thinking_chars), cap))
         if json_schema is not None and hasattr(eng, "compile_schema"):
-            longest = eng.compile_schema(json_schema).longest_path()
+            longest = eng.compile_schema(json_schema, limits).longest_path()
             if longest is not None:
                 return int(min(max(longest, 8), cap))
         return int(min(512, cap))
@@ -270,7 +274,7 @@ class Sutro(Templates, BaseSutroClient):
             if str(model).endswith("-thinking") and not getattr(eng.spec, "embedding_model", False):
                 thinking = int(sp.get("max_thinking_chars", 128))
             if max_new is None:
-                max_new = self._default_max_new_tokens(eng, json_schema, thinking)
+                max_new = self._default_max_new_tokens(eng, json_schema, thinking, self.fsm_limits)
             t0 = time.perf_counter()
             stream = None
             if self.on_progress is not None or (stay_attached and self.verbose):
@@ -283,6 +287,8 @@ class Sutro(Templates, BaseSutroClient):
                       return_logprobs=True, progress=stream)
             if thinking is not None:
                 kw["thinking_chars"] = thinking
+            if self.fsm_limits is not None:
+                kw["fsm_limits"] = self.fsm_limits
             res = self._dispatch(eng, input_data, kw)
             if res is None:          # a non-source rank of a row-sharded job: nothing to report
                 job.status = JobStatus.SUCCEEDED

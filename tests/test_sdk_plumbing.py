@@ -530,3 +530,35 @@ def test_thinking_models_report_content_and_reasoning():
     # a non-thinking model name does not ask for a thinking turn
     c.infer(["a"], model="qwen-3-4b", output_schema=Sentiment, stay_attached=False)
     assert "thinking_chars" not in eng.calls[-1][1]
+
+
+def test_client_fsm_limits_reach_the_engine_and_the_output_budget():
+    """Strings a schema leaves unbounded stop at FsmLimits.max_string_chars (64 by default; the
+    hosted service has no such cap) — the client option raises it, and the default output
+    budget follows the longer automaton."""
+    from sutro_b200.schema_fsm import FsmLimits, compile_schema
+    from sutro_b200.sdk import Sutro
+
+    schema = {"type": "object", "properties": {"note": {"type": "string"}}, "required": ["note"]}
+    seen = {}
+
+    class Eng:
+        spec = None
+
+        def compile_schema(self, sch, limits=None, thinking_chars=None):
+            seen.setdefault("compile", []).append(limits)
+            return compile_schema(sch, limits)
+
+        def generate(self, rows, **kw):
+            import types
+            seen["kw"] = kw
+            return types.SimpleNamespace(outputs=['{"note":"x"}'] * len(rows), embeddings=None,
+                                         stats={}, cum_logprobs=None)
+
+    wide = FsmLimits(max_string_chars=300)
+    c = Sutro(verbose=False, fsm_limits=wide)
+    c.register_engine("qwen-3-4b", Eng())
+    jid = c.infer(["a", "b"], model="qwen-3-4b", output_schema=schema, stay_attached=False)
+    assert jid is not None and seen["kw"]["fsm_limits"] is wide and seen["compile"][-1] is wide
+    narrow_budget = compile_schema(schema).longest_path()
+    assert seen["kw"]["max_new_tokens"] == compile_schema(schema, wide).longest_path() > narrow_budget
