@@ -1,6 +1,6 @@
 """Turn the .ncu-rep files a GPU run left in gpurun_out/ into the small, committed evidence
 under profiles/:
-    python tools/profile_extract.py gpurun_out/prof_prefill_step_r02.ncu-rep profiles/r02_ncu_prefill_step.csv
+    python tools/profile_extract.py gpurun_out/r02_ncu_prefill_step_raw.csv profiles/r02_ncu_prefill_step.csv
 writes one row per captured launch with the columns the roofline discussion uses (duration,
 DRAM bytes, tensor-pipe %, L2 hit rate, registers, grid, achieved occupancy, top stall reasons)."""
 import csv
