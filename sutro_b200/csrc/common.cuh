@@ -301,6 +301,68 @@ SB_DEVICE void tc_mma_f16_cta2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- one K block per asm statement -------------------------------------------------------
+// The thread that issues tcgen05.mma is alone on its job: per 64-element K block the tensor
+// pipe needs 512 cycles (128x256x64 per SM) and the thread must get four MMAs and a commit out
+// in less.  Written as five separate asm statements with 64-bit descriptor operands that costs
+// ~124 SASS instructions (ptxas moves every operand into uniform registers with an ELECT +
+// R2UR.BROADCAST round trip per instruction and does the 64-bit descriptor arithmetic in
+// register pairs) — at the IPC one warp reaches that IS the 512 cycles, and ncu showed the issuing
+// thread busy 85 % of the time with the tensor pipe 84 % active.  Here the descriptor's high
+// word is an immediate (SBO = 1024 B, version 1, SWIZZLE_128B: constant for every K-major
+// SW128 tile), only the low words (start address | LBO) travel, and the +32-byte K steps are
+// 32-bit adds.
+constexpr uint32_t kDescHiKSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // = 0x40004040
+SB_DEVICE uint32_t umma_desc_lo_k_sw128(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+#define SB_KBLOCK4_BODY(GROUP)                                                               \
+  ".reg .pred p;\n"                                                                          \
+  ".reg .b64 da, db;\n"                                                                      \
+  ".reg .b32 al, bl;\n"                                                                      \
+  "setp.ne.b32 p, %4, 0;\n"                                                                  \
+  "mov.b64 da, {%1, %5};\n"                                                                  \
+  "mov.b64 db, {%2, %5};\n"                                                                  \
+  "tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], da, db, %3, p;\n"                        \
+  "setp.ne.b32 p, 1, 0;\n"                                                                   \
+  "add.u32 al, %1, 2;\n"                                                                     \
+  "add.u32 bl, %2, 2;\n"                                                                     \
+  "mov.b64 da, {al, %5};\n"                                                                  \
+  "mov.b64 db, {bl, %5};\n"                                                                  \
+  "tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], da, db, %3, p;\n"                        \
+  "add.u32 al, %1, 4;\n"                                                                     \
+  "add.u32 bl, %2, 4;\n"                                                                     \
+  "mov.b64 da, {al, %5};\n"                                                                  \
+  "mov.b64 db, {bl, %5};\n"                                                                  \
+  "tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], da, db, %3, p;\n"                        \
+  "add.u32 al, %1, 6;\n"                                                                     \
+  "add.u32 bl, %2, 6;\n"                                                                     \
+  "mov.b64 da, {al, %5};\n"                                                                  \
+  "mov.b64 db, {bl, %5};\n"                                                                  \
+  "tcgen05.mma.cta_group::" GROUP ".kind::f16 [%0], da, db, %3, p;\n"
+// Four K=16 steps of one SW128 K block (A, B both K-major) + the commit that frees the stage.
+// Called by the ONE issuing thread.
+SB_DEVICE void tc_mma_kblock4_cta2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                   uint32_t accumulate_first, uint32_t empty_bar, uint16_t mask) {
+  asm volatile(
+      "{\n" SB_KBLOCK4_BODY("2")
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%6], %7;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "n"(kDescHiKSw128), "r"(empty_bar),
+      "h"(mask)
+      : "memory");
+}
+SB_DEVICE void tc_mma_kblock4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                              uint32_t accumulate_first, uint32_t empty_bar) {
+  asm volatile(
+      "{\n" SB_KBLOCK4_BODY("1")
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "n"(kDescHiKSw128), "r"(empty_bar)
+      : "memory");
+}
+#undef SB_KBLOCK4_BODY
 // commit: arrive on the barrier at this offset in every CTA of `mask`
 SB_DEVICE void tc_commit_cta2_mc(uint32_t bar, uint16_t mask) {
   asm volatile(

@@ -344,6 +344,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
   } else if (warp == 1) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+    const uint32_t a_lo0 = umma_desc_lo_k_sw128(smem_u32(smem));   // stage 0's A tile
+    const uint32_t empty0 = smem_u32(&empty_bar[0]);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -356,16 +358,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::kABytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the swizzle span: +2 in 16-byte units
-            tc_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          }
-          tc_commit(smem_u32(&empty_bar[stage]));
-          if (kb == num_k - 1) tc_commit(smem_u32(&tfull_bar[acc]));
+          static_assert(kBlockK / kUmmaK == 4, "tc_mma_kblock4 issues four K=16 steps");
+          const uint32_t a_lo = a_lo0 + stage * (Cfg::kStageBytes >> 4);
+          tc_mma_kblock4(tmem_d, a_lo, a_lo + (Cfg::kABytes >> 4), idesc, kb != 0,
+                         empty0 + stage * 8);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -373,6 +369,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
           phase ^= 1;
         }
       }
+      // the accumulator is complete when every MMA issued so far has retired
+      if (lane == 0) tc_commit(smem_u32(&tfull_bar[acc]));
+      __syncwarp();
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;
@@ -530,6 +529,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
     // ===== MMA issuer (leader CTA only) =====
     if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, k2BlockN);
+      const uint32_t a_lo0 = umma_desc_lo_k_sw128(smem_u32(smem));   // stage 0's A tile
+      const uint32_t empty0 = smem_u32(&empty_bar[0]);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -542,14 +543,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * k2StageBytes);
-            const uint64_t adesc = umma_desc_k_sw128(sa);
-            const uint64_t bdesc = umma_desc_k_sw128(sa + k2HalfBytes);
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              tc_mma_f16_cta2(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            tc_commit_cta2_mc(smem_u32(&empty_bar[stage]), 0x3);
-            if (kb == num_k - 1) tc_commit_cta2_mc(smem_u32(&tfull_bar[acc]), 0x3);
+            static_assert(kBlockK / kUmmaK == 4, "tc_mma_kblock4 issues four K=16 steps");
+            const uint32_t a_lo = a_lo0 + stage * (k2StageBytes >> 4);
+            tc_mma_kblock4_cta2(tmem_d, a_lo, a_lo + (k2HalfBytes >> 4), idesc, kb != 0,
+                                empty0 + stage * 8, 0x3);
           }
           __syncwarp();
           if (++stage == k2Stages) {
@@ -557,6 +554,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
             phase ^= 1;
           }
         }
+        // the accumulator is complete when every MMA issued so far has retired
+        if (lane == 0) tc_commit_cta2_mc(smem_u32(&tfull_bar[acc]), 0x3);
+        __syncwarp();
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1;
@@ -854,13 +854,14 @@ int gemm_bf16_tn(const void* a, int a_rows, const void* w, void* d, const void* 
   }
   if (block_n == 0) {
     block_n = gemm_pick_block_n(M, N);
-    // The wide gate/up projection (N = 2*d_ff) runs on the one-CTA 128x256 kernel: measured
-    // ahead of the CTA pair on that shape both in isolation (1553 vs 1502 TFLOP/s at M = 32768)
-    // and inside the benchmark step (-1.7 % GEMM time).  Every tile shape accumulates in the
-    // same order, so this choice changes no result.  SB200_GEMM_SWIGLU_BN=512 restores the pair.
+    // The wide gate/up projection (N = 2*d_ff) also runs on the CTA pair: once the issue loop
+    // stopped being the limiter the pair leads the one-CTA 128x256 tile on that shape too
+    // (1411 vs 1352 TFLOP/s sustained at M = 32768, tools/gemm_sustained.py).  Every tile
+    // shape accumulates in the same order, so this choice changes no result.
+    // SB200_GEMM_SWIGLU_BN=256 selects the one-CTA tile for comparison.
     static const int swiglu_bn = [] {
       const char* e = getenv("SB200_GEMM_SWIGLU_BN");
-      return e ? atoi(e) : 256;
+      return e ? atoi(e) : 512;
     }();
     if (epilogue == EPI_SWIGLU_BF16 && block_n == 512 && N >= 8192 &&
         (swiglu_bn == 256 || swiglu_bn == 512))
