@@ -151,6 +151,23 @@ SB_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// For waits that last microseconds (an epilogue warp waiting for its tile, a producer that is a
+// full ring ahead): the same wait with a suspend-time hint, so the thread sleeps in the barrier
+// unit instead of re-issuing the poll; it is woken when the phase completes.
+SB_DEVICE void mbar_wait_long(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+  } while (!done);
+}
 
 // ---------------------------------------------------------------------------
 // TMA
@@ -360,6 +377,15 @@ SB_DEVICE void tc_mma_kblock4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uin
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n"
       "}\n" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "n"(kDescHiKSw128), "r"(empty_bar)
+      : "memory");
+}
+// the same four steps without a commit: the first half of a two-span (K = 128) stage
+SB_DEVICE void tc_mma_kblock4_cta2_nocommit(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                            uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n" SB_KBLOCK4_BODY("2")
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "n"(kDescHiKSw128)
       : "memory");
 }
 #undef SB_KBLOCK4_BODY

@@ -327,7 +327,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
         int m_blk, n_blk;
         tile_to_mn(ea_gm, tile, num_m, num_n, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          mbar_wait_long(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb_ = sa + Cfg::kABytes;
@@ -390,7 +390,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       const bool row_ok = row < M;
       QkvRowMeta rm;
       if constexpr (EPI == EPI_QKV_ROPE) qkv_row_meta(ea, row, row_ok, part, rm);  // overlaps the mainloop
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      mbar_wait_long(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       if constexpr (EPI == EPI_QKV_ROPE) {
         static_assert(BLOCK_N % 128 == 0 || EPI != EPI_QKV_ROPE, "fused QKV needs whole heads");
@@ -448,7 +448,10 @@ constexpr int k2StageBytes = 2 * k2HalfBytes;       // A half-tile + B half-tile
 constexpr int k2BlockN = 256;
 constexpr int k2SmemBytes(int stages) { return stages * k2StageBytes + 256 + 1024; }
 
-template <int EPI, int k2Stages>
+// KSUB 64-element K spans share one pipeline stage (one full / one empty barrier): with
+// KSUB = 2 the issuing thread and the producer pay the barrier round trip once per 128 K
+// elements (8 MMAs).  k2Stages counts stages, so shared memory holds k2Stages * KSUB spans.
+template <int EPI, int k2Stages, int KSUB = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
                      const __grid_constant__ CUtensorMap tm_b, void* __restrict__ d_out,
@@ -459,7 +462,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
   // same in every CTA of a kernel, so the alignment fix-up below is identical too.
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  constexpr int kStageBytes = KSUB * k2StageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * kStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + k2Stages;
   uint64_t* tfull_bar = bars + 2 * k2Stages;
@@ -498,7 +502,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
   const int num_m = (M + 255) / 256;
   const int num_n = (N + k2BlockN - 1) / k2BlockN;
   const int num_tiles = num_m * num_n;
-  const int num_k = K / kBlockK;
+  const int num_k = K / (kBlockK * KSUB);
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
@@ -511,13 +515,18 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
         int m_blk, n_blk;
         tile_to_mn(ea_gm, tile, num_m, num_n, m_blk, n_blk);
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          mbar_wait_long(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb_leader = smem_u32(&full_bar[stage]) & kPeerBitMask;
-          const uint32_t sa = smem_u32(smem + stage * k2StageBytes);
-          if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * k2StageBytes);
-          tma_load_2d_cta2(sa, &tm_a, fb_leader, kb * kBlockK, m_blk * 256 + rank * 128);
-          tma_load_2d_cta2(sa + k2HalfBytes, &tm_b, fb_leader, kb * kBlockK,
-                           n_blk * k2BlockN + rank * 128);
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), 2 * kStageBytes);
+#pragma unroll
+          for (int sub = 0; sub < KSUB; ++sub) {
+            const int k0 = (kb * KSUB + sub) * kBlockK;
+            tma_load_2d_cta2(sa + sub * k2StageBytes, &tm_a, fb_leader, k0,
+                             m_blk * 256 + rank * 128);
+            tma_load_2d_cta2(sa + sub * k2StageBytes + k2HalfBytes, &tm_b, fb_leader, k0,
+                             n_blk * k2BlockN + rank * 128);
+          }
           if (++stage == k2Stages) {
             stage = 0;
             phase ^= 1;
@@ -544,9 +553,13 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
           tc_fence_after();
           if (lane == 0) {
             static_assert(kBlockK / kUmmaK == 4, "tc_mma_kblock4 issues four K=16 steps");
-            const uint32_t a_lo = a_lo0 + stage * (k2StageBytes >> 4);
-            tc_mma_kblock4_cta2(tmem_d, a_lo, a_lo + (k2HalfBytes >> 4), idesc, kb != 0,
-                                empty0 + stage * 8, 0x3);
+            uint32_t a_lo = a_lo0 + stage * (kStageBytes >> 4);
+#pragma unroll
+            for (int sub = 0; sub + 1 < KSUB; ++sub, a_lo += k2StageBytes >> 4)
+              tc_mma_kblock4_cta2_nocommit(tmem_d, a_lo, a_lo + (k2HalfBytes >> 4), idesc,
+                                           (kb | sub) != 0);
+            tc_mma_kblock4_cta2(tmem_d, a_lo, a_lo + (k2HalfBytes >> 4), idesc,
+                                (kb != 0) || KSUB > 1, empty0 + stage * 8, 0x3);
           }
           __syncwarp();
           if (++stage == k2Stages) {
@@ -576,7 +589,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a,
       const bool row_ok = row < M;
       QkvRowMeta rm;
       if constexpr (EPI == EPI_QKV_ROPE) qkv_row_meta(ea, row, row_ok, part, rm);  // overlaps the mainloop
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      mbar_wait_long(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       if constexpr (EPI == EPI_QKV_ROPE) {
 #pragma unroll 1
@@ -775,17 +788,17 @@ int launch_cfg(const void* a, int a_rows, const void* w, void* d, const void* re
   return 0;
 }
 
-template <int EPI, int STAGES>
+template <int EPI, int STAGES, int KSUB = 1>
 int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* resid, int M, int N,
                 int K, int ldd, cudaStream_t stream, const QkvEpiArgs& ea) {
   CUtensorMap tm_a, tm_b;
   if (make_tmap(a, a_rows, K, 128, &tm_a)) return -1;
   if (make_tmap(w, N, K, 128, &tm_b)) return -1;
-  auto kern = gemm2_bf16_tn_kernel<EPI, STAGES>;
-  SB_SET_MAX_SMEM(kern, k2SmemBytes(STAGES));
+  auto kern = gemm2_bf16_tn_kernel<EPI, STAGES, KSUB>;
+  SB_SET_MAX_SMEM(kern, k2SmemBytes(STAGES * KSUB));
   const int tiles = ((M + 255) / 256) * ((N + k2BlockN - 1) / k2BlockN);
   const int clusters = std::min(tiles, num_sms() / 2);
-  kern<<<2 * clusters, gemm_threads<EPI>(), k2SmemBytes(STAGES), stream>>>(
+  kern<<<2 * clusters, gemm_threads<EPI>(), k2SmemBytes(STAGES * KSUB), stream>>>(
       tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd,
       raster_group(256, N, K), ea);
   SB_CUDA_CHECK(cudaGetLastError());
@@ -796,10 +809,20 @@ template <int EPI>
 int launch_epi(int block_n, const void* a, int a_rows, const void* w, void* d, const void* resid,
                int M, int N, int K, int ldd, cudaStream_t stream, const QkvEpiArgs& ea) {
   switch (block_n) {
-    case 512:  // CTA-pair kernel: 256x256 tile per 2-CTA cluster
+    case 512: {  // CTA-pair kernel: 256x256 tile per 2-CTA cluster
+      // K = 128 per pipeline stage (3 stages of two 64-element spans) when K allows it: half
+      // the barrier round trips per MMA for the issuing thread.  SB200_GEMM_KSUB=1 keeps the
+      // 7 x 64 ring.  The K order of the accumulation is the same either way.
+      static const int ksub = [] {
+        const char* e = getenv("SB200_GEMM_KSUB");
+        return e ? atoi(e) : 1;   // measured: 3 x 128 trails 7 x 64 by 1-2 % (shallower ring)
+      }();
+      if (ksub == 2 && K % (2 * kBlockK) == 0)
+        return launch_cta2<EPI, 3, 2>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
       return launch_cta2<EPI, 7>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
-    case 516:  // experiment knobs (tools/gemm_bench.py): same kernel, shallower rings
-      return launch_cta2<EPI, 6>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
+    }
+    case 516:  // experiment knobs (tools/gemm_bench.py): the 7 x 64 ring, a shallower ring
+      return launch_cta2<EPI, 7>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     case 514:
       return launch_cta2<EPI, 4>(a, a_rows, w, d, resid, M, N, K, ldd, stream, ea);
     case 64:
