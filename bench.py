@@ -672,10 +672,11 @@ def main():
                     "bound": "tensor", "achieved": kb["gemm_tflops"],
                     "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": kb["gemm_frac_of_sustained_peak"],
-                    "traffic": ncu_traffic("r02_ncu_prefill_step.csv", "gemm_bf16_tn_kernel<256, 2>"),
+                    "traffic": ncu_traffic("r02_ncu_prefill_step.csv", "gemm2_bf16_tn_kernel<2, 7"),
                     "traffic_note": "bytes of ONE gate/up GEMM launch of a full prefill step "
                                     "(M=32670, N=19456, K=2560; algorithmic 903 MB = A 167 + "
-                                    "W 100 + SwiGLU output 636) from the committed capture "
+                                    "W 100 + SwiGLU output 636; W does not fit L2, so A and W "
+                                    "are re-read) from the committed capture "
                                     "profiles/r02_ncu_prefill_step.csv, not from this run",
                     "peak_source": pk["source"] + " (sustained: kernel timed inside a long step)",
                     "share_of_step": kb["share"]["gemm"],

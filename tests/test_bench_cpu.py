@@ -24,8 +24,8 @@ def test_host_helpers():
     rows = synth.product_reviews(500, seed=0)
     p = bench.plumbing_cost("qwen-3-4b", rows, ['{"sentiment":"positive"}'] * len(rows))
     assert p["rows"] == 500 and p["rows_per_s"] > 0 and p["payload_bytes"] > 500
-    t = bench.ncu_traffic("r02_ncu_prefill_step.csv", "gemm_bf16_tn_kernel<256, 2>")
-    assert t is not None and 0.9e9 < t < 2e9         # one gate/up launch: ~0.9 GB algorithmic
+    t = bench.ncu_traffic("r02_ncu_prefill_step.csv", "gemm2_bf16_tn_kernel<2, 7")
+    assert t is not None and 0.9e9 < t < 2.5e9       # one gate/up launch: ~0.9 GB algorithmic
     t = bench.ncu_traffic("r02_ncu_decode_side.csv", "attn_decode_warp_kernel")
     assert t is not None and t > 1e8
     assert bench.ncu_traffic("does_not_exist.csv", "x") is None

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
+# sustained-rate scan of experiment knobs on the N = 2560 shapes (one process per setting)
 set -u
-mkdir -p gpurun_out
-timeout -k 10 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "gemm or qkv_rope" -p no:cacheprovider 2>&1 | tail -3
-if [ ${PIPESTATUS[0]} -ne 0 ]; then echo "KERNEL TESTS FAILED - stopping"; exit 1; fi
-timeout 200 python tools/gemm_sustained.py 32768 --secs 2 --variants 512
+for c in 74 72 70 64; do for g in 1 2; do
+  SB200_GEMM_CLUSTERS=$c SB200_GEMM_GM=$g timeout 120 python tools/gemm_sustained.py 32768 --secs 2 --shapes wo,down --variants 512 --no-cublas
+done; done
