@@ -797,12 +797,7 @@ int launch_cta2(const void* a, int a_rows, const void* w, void* d, const void* r
   auto kern = gemm2_bf16_tn_kernel<EPI, STAGES, KSUB>;
   SB_SET_MAX_SMEM(kern, k2SmemBytes(STAGES * KSUB));
   const int tiles = ((M + 255) / 256) * ((N + k2BlockN - 1) / k2BlockN);
-  static const int forced_clusters = [] {   // SB200_GEMM_CLUSTERS: experiment knob
-    const char* e = getenv("SB200_GEMM_CLUSTERS");
-    return e ? atoi(e) : 0;
-  }();
-  int clusters = std::min(tiles, num_sms() / 2);
-  if (forced_clusters > 0) clusters = std::min(clusters, forced_clusters);
+  const int clusters = std::min(tiles, num_sms() / 2);
   kern<<<2 * clusters, gemm_threads<EPI>(), k2SmemBytes(STAGES * KSUB), stream>>>(
       tm_a, tm_b, d, reinterpret_cast<const __nv_bfloat16*>(resid), M, N, K, ldd,
       raster_group(256, N, K), ea);
