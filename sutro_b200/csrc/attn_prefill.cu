@@ -274,14 +274,6 @@ int attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t
                    kPfMaxPages);
     return -1;
   }
-  // opt-in variant (attn_prefill_v2.cu): decoupled warps, Q through shared memory
-  static const bool use_v2 = [] {
-    const char* e = std::getenv("SB200_PREFILL_V2");
-    return e != nullptr && e[0] == '1';
-  }();
-  if (use_v2)
-    return attn_prefill_v2(qkv, out, kv_layer, page_table, max_pages, work, n_work, seq_slot,
-                           seq_q_start, seq_q_len, seq_past, hq, hkv, scale, stream);
 #define SB_PF(G)                                                                               \
   return launch<G>(qkv, out, kv_layer, page_table, max_pages, work, n_work, seq_slot,         \
                    seq_q_start, seq_q_len, seq_past, hq, hkv, scale, stream)

@@ -87,11 +87,6 @@ int attn_prefill(const void* qkv, void* out, const void* kv_layer, const int32_t
                  const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past,
                  int hq, int hkv, float scale, cudaStream_t stream);
 int attn_prefill_q_tile(int hq, int hkv);
-// opt-in variant selected inside attn_prefill() when SB200_PREFILL_V2=1 (same arguments)
-int attn_prefill_v2(const void* qkv, void* out, const void* kv_layer, const int32_t* page_table,
-                    int max_pages, const int32_t* work, int n_work, const int32_t* seq_slot,
-                    const int32_t* seq_q_start, const int32_t* seq_q_len, const int32_t* seq_past,
-                    int hq, int hkv, float scale, cudaStream_t stream);
 
 // K3 (tcgen05) — causal prefill attention over DENSE K/V: new tokens' K/V are the k/v columns
 // of the qkv buffer itself (post-norm/RoPE, written by the fused QKV epilogue), the shared
