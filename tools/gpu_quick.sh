@@ -1,0 +1,4 @@
+#!/usr/bin/env bash
+set -u
+timeout 300 python -m pytest tests/test_kernels_gpu.py tests/test_public_api_gpu.py -q -p no:cacheprovider 2>&1 | tail -3
+timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
