@@ -114,6 +114,14 @@ int sb200_fsm_build_mask(const int32_t* fsm_trans, const uint8_t* fsm_accept, in
 int sb200_tokenizer_create(const int32_t* merges, int n_merges, const int32_t* merged_ids,
                            const uint8_t* cls_table, int digits, const uint8_t* tok_bytes,
                            const int32_t* tok_off, int vocab, void** out);
+/* `ignore_merges` of a tokenizer file (tokenizers' BPE: a pre-token that is itself in the
+ * vocabulary is emitted as that token without running the merges; Llama-3 files set it).
+ * The caller lists the vocabulary entries whose merges do NOT rebuild them: entry ids[i] and the
+ * token sequence seq_tokens[seq_off[i] .. seq_off[i+1]) its merges produce (2..32 tokens).  A
+ * pre-token that merges to one of these sequences is then emitted as ids[i].  n = 0 clears.
+ * Host pointers. */
+int sb200_tokenizer_set_word_overrides(void* tok, const int32_t* seq_tokens, const int32_t* seq_off,
+                                       const int32_t* ids, int n);
 void sb200_tokenizer_destroy(void* tok);
 int sb200_tokenizer_encode(void* tok, const uint8_t* text_dev, int64_t n_bytes,
                            const int64_t* row_off_dev, int64_t n_rows, int32_t* out_tokens_dev,

@@ -6,8 +6,10 @@ no tokenizer).  Algorithm restated: byte-level BPE as implemented
 `tokenizers` 0.22.2 library (third-party, pinned by this image) — pre-tokenise with the
 published GPT-4-style pattern (sutro_b200/vocab.py PRETOK_PATTERN), then inside each
 pre-token repeatedly merge the adjacent pair with the lowest merge rank, leftmost first
-(tokenizers/src/models/bpe/word.rs `merge_all`).  tests/test_tokenizer_oracle.py pins
-this restatement against `tokenizers` itself on the same vocabulary.
+(tokenizers/src/models/bpe/word.rs `merge_all`); with the model's `ignore_merges` flag a
+pre-token that is itself a vocabulary entry is emitted as that token without merging
+(tokenizers/src/models/bpe/model.rs `tokenize_with_cache`).  tests/test_tokenizer_oracle.py
+pins this restatement against `tokenizers` itself on the same vocabulary, flag off and on.
 """
 from __future__ import annotations
 
@@ -25,8 +27,17 @@ class RefTokenizer:
         self.rank: Dict[Tuple[int, int], Tuple[int, int]] = {}
         for i, (a, b) in enumerate(v.merges):
             self.rank.setdefault((a, b), (i, 256 + i if v.merged_ids is None else v.merged_ids[i]))
+        # ignore_merges: whole pre-token -> id, over the model vocabulary (not the added tokens)
+        self.whole: Dict[bytes, int] = {}
+        if v.word_overrides is not None:
+            special_ids = set(v.specials.values())
+            for i, tb in enumerate(v.token_bytes):
+                if tb and i not in special_ids:
+                    self.whole.setdefault(tb, i)
 
     def _bpe(self, word: bytes) -> List[int]:
+        if word in self.whole:
+            return [self.whole[word]]
         s = list(word)
         while len(s) > 1:
             best, bi = None, -1

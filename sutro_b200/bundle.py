@@ -57,6 +57,12 @@ def export_bundle(engine, out_dir: str) -> str:
         put("tok.cls_table", np.ascontiguousarray(class_table(), dtype=np.uint8))
         put("tok.bytes", np.ascontiguousarray(blob, dtype=np.uint8))
         put("tok.offsets", np.ascontiguousarray(off, dtype=np.int32))
+        if v.word_overrides:      # ignore_merges (vocab.Vocab.word_overrides)
+            from .engine import word_override_arrays
+            o_toks, o_off, o_ids = word_override_arrays(v)
+            put("tok.override_tokens", o_toks)
+            put("tok.override_offsets", o_off)
+            put("tok.override_ids", o_ids)
     manifest = {
         "format": 1,
         "spec": {"name": spec.name, "family": spec.family, "n_layers": spec.n_layers,

@@ -131,6 +131,10 @@ int sb200_tokenizer_create(const int32_t* merges, int n_merges, const int32_t* m
   *out = t;
   return rc;
 }
+int sb200_tokenizer_set_word_overrides(void* tok, const int32_t* seq_tokens, const int32_t* seq_off,
+                                       const int32_t* ids, int n) {
+  return tokenizer_set_word_overrides(static_cast<Tokenizer*>(tok), seq_tokens, seq_off, ids, n);
+}
 void sb200_tokenizer_destroy(void* tok) { tokenizer_destroy(static_cast<Tokenizer*>(tok)); }
 int sb200_tokenizer_encode(void* tok, const uint8_t* text_dev, int64_t n_bytes,
                            const int64_t* row_off_dev, int64_t n_rows, int32_t* out_tokens_dev,

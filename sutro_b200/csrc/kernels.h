@@ -155,6 +155,8 @@ struct Tokenizer;
 int tokenizer_create(const int32_t* merges, int n_merges, const int32_t* merged_ids,
                      const uint8_t* cls_table, int digits, const uint8_t* tok_bytes,
                      const int32_t* tok_off, int vocab, Tokenizer** out);
+int tokenizer_set_word_overrides(Tokenizer* t, const int32_t* seq_tokens, const int32_t* seq_off,
+                                 const int32_t* ids, int n);
 void tokenizer_destroy(Tokenizer* t);
 const uint8_t* tokenizer_tok_bytes(const Tokenizer* t);
 const int32_t* tokenizer_tok_off(const Tokenizer* t);

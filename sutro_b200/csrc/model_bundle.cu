@@ -344,6 +344,19 @@ int sb200_model_open(const char* dir, int device, int max_slots, int max_prefill
                                reinterpret_cast<const uint8_t*>(tokb),
                                reinterpret_cast<const int32_t*>(toko), c.vocab, &m->tokenizer))
       return -1;
+    if (tens->has("tok.override_ids")) {   // the tokenizer file sets ignore_merges
+      const char *ot, *oo, *oi;
+      int64_t nb_ot, nb_oo, nb_oi;
+      region("tok.override_tokens", &ot, &nb_ot);
+      region("tok.override_offsets", &oo, &nb_oo);
+      region("tok.override_ids", &oi, &nb_oi);
+      if (nb_oo != nb_oi + 4) json::fail("manifest: tok.override_offsets has the wrong size");
+      if (sb200_tokenizer_set_word_overrides(m->tokenizer, reinterpret_cast<const int32_t*>(ot),
+                                             reinterpret_cast<const int32_t*>(oo),
+                                             reinterpret_cast<const int32_t*>(oi),
+                                             static_cast<int>(nb_oi / 4)))
+        return -1;
+    }
     if (sb200_engine_set_vocab(m->engine, reinterpret_cast<const uint8_t*>(tokb),
                                reinterpret_cast<const int32_t*>(toko)))
       return -1;

@@ -10,6 +10,11 @@
 //      then repeatedly merges the lowest-rank adjacent pair (leftmost on ties)
 //      using an open-addressing hash of (left,right)->(rank,id) (8 MB, L2
 //      resident), in place in a scratch array; records the token count.
+//      Optional whole-word overrides (`ignore_merges` of Llama-3 tokenizer files: a pre-token
+//      that is itself a vocabulary entry is emitted as that token even when its merges would
+//      build something else): the host lists, for every such entry, the sequence its merges DO
+//      build; a pre-token whose merge result equals one of those sequences is replaced by the
+//      entry's id (two byte strings never merge to the same tokens, so the match is exact).
 //   3. exclusive scan (CUB) of the counts + compaction into the output.
 // HBM traffic: text bytes in, 4 B per token out, plus scratch at 4 B per byte.
 #include <cub/device/device_scan.cuh>
@@ -32,9 +37,25 @@ struct TokTables {
   uint32_t hmask;
   const int32_t* byte_to_id; // [256]
   int digits;
+  // whole-word overrides (fmask == 0: none): open-addressing table keyed by seq_hash
+  const uint64_t* fkeys;     // [fmask + 1]
+  const int4* fslots;        // {id, arena offset, length, 0}
+  const int32_t* farena;     // the sequences, back to back
+  uint32_t fmask;
 };
 
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kOverrideMaxLen = 32;
+
+__host__ __device__ inline uint64_t seq_hash(const int32_t* s, int n) {   // FNV-1a over the ids
+  uint64_t h = 0xCBF29CE484222325ull ^ static_cast<uint64_t>(n);
+  for (int i = 0; i < n; ++i) {
+    h ^= static_cast<uint32_t>(s[i]);
+    h *= 0x100000001B3ull;
+  }
+  h ^= h >> 29;
+  return h == kEmptyKey ? 0 : h;
+}
 
 __host__ __device__ inline uint32_t pair_hash(uint32_t a, uint32_t b) {
   uint32_t h = a * 0x9E3779B1u;
@@ -220,6 +241,25 @@ bpe_kernel(TokTables tb, const uint8_t* __restrict__ text, int64_t n_bytes,
     for (int i = best_i + 1; i + 1 < n; ++i) s[i] = s[i + 1];
     --n;
   }
+  if (tb.fmask != 0 && n >= 2 && n <= kOverrideMaxLen) {   // whole-word override?
+    const uint64_t key = seq_hash(s, n);
+    uint32_t h = static_cast<uint32_t>(key) & tb.fmask;
+    while (true) {
+      const uint64_t k = tb.fkeys[h];
+      if (k == kEmptyKey) break;
+      if (k == key) {
+        const int4 sl = tb.fslots[h];
+        bool same = sl.z == n;
+        for (int i = 0; same && i < n; ++i) same = tb.farena[sl.y + i] == s[i];
+        if (same) {
+          s[0] = sl.x;
+          n = 1;
+          break;
+        }
+      }
+      h = (h + 1) & tb.fmask;
+    }
+  }
   cnt[pos] = n;
 }
 
@@ -283,6 +323,11 @@ struct Tokenizer {
   uint8_t* d_tok_bytes = nullptr;
   int32_t* d_tok_off = nullptr;
   int vocab = 0;
+  // whole-word overrides (tokenizer_set_word_overrides)
+  uint64_t* d_fkeys = nullptr;
+  int4* d_fslots = nullptr;
+  int32_t* d_farena = nullptr;
+  uint32_t fmask = 0;
   // growable scratch
   int64_t cap = 0;
   uint8_t* d_flags = nullptr;
@@ -299,6 +344,9 @@ struct Tokenizer {
     cudaFree(d_byte_to_id);
     cudaFree(d_tok_bytes);
     cudaFree(d_tok_off);
+    cudaFree(d_fkeys);
+    cudaFree(d_fslots);
+    cudaFree(d_farena);
     cudaFree(d_flags);
     cudaFree(d_sym);
     cudaFree(d_cnt);
@@ -382,6 +430,48 @@ int tokenizer_create(const int32_t* merges, int n_merges, const int32_t* merged_
   return 0;
 }
 
+// n sequences (seq_off[n+1] into seq_tokens), each the merge result of the vocabulary entry
+// ids[i]; n == 0 clears the table.  Replaces any previous table.
+int tokenizer_set_word_overrides(Tokenizer* t, const int32_t* seq_tokens, const int32_t* seq_off,
+                                 const int32_t* ids, int n) {
+  cudaFree(t->d_fkeys);
+  cudaFree(t->d_fslots);
+  cudaFree(t->d_farena);
+  t->d_fkeys = nullptr, t->d_fslots = nullptr, t->d_farena = nullptr, t->fmask = 0;
+  if (n <= 0) return 0;
+  uint32_t capn = 64;
+  while (capn < static_cast<uint32_t>(n) * 2u + 16u) capn <<= 1;
+  std::vector<uint64_t> keys(capn, kEmptyKey);
+  std::vector<int4> slots(capn, make_int4(0, 0, 0, 0));
+  for (int i = 0; i < n; ++i) {
+    const int off = seq_off[i], len = seq_off[i + 1] - seq_off[i];
+    if (len < 2 || len > kOverrideMaxLen || ids[i] < 0 || ids[i] >= t->vocab) {
+      set_last_error("tokenizer: word override %d has length %d (2..%d supported) or a bad id", i,
+                     len, kOverrideMaxLen);
+      return -1;
+    }
+    const uint64_t key = seq_hash(seq_tokens + off, len);
+    uint32_t h = static_cast<uint32_t>(key) & (capn - 1);
+    while (keys[h] != kEmptyKey) h = (h + 1) & (capn - 1);
+    keys[h] = key;
+    slots[h] = make_int4(ids[i], off, len, 0);
+  }
+  const size_t arena = static_cast<size_t>(seq_off[n]) * sizeof(int32_t);
+  if (cudaMalloc(&t->d_fkeys, capn * 8ull) != cudaSuccess ||
+      cudaMalloc(&t->d_fslots, capn * sizeof(int4)) != cudaSuccess ||
+      cudaMalloc(&t->d_farena, arena) != cudaSuccess) {
+    set_last_error("tokenizer: cudaMalloc of the override table failed: %s",
+                   cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  cudaMemcpy(t->d_fkeys, keys.data(), capn * 8ull, cudaMemcpyHostToDevice);
+  cudaMemcpy(t->d_fslots, slots.data(), capn * sizeof(int4), cudaMemcpyHostToDevice);
+  cudaMemcpy(t->d_farena, seq_tokens, arena, cudaMemcpyHostToDevice);
+  SB_CUDA_CHECK(cudaGetLastError());
+  t->fmask = capn - 1;
+  return 0;
+}
+
 void tokenizer_destroy(Tokenizer* t) { delete t; }
 
 const uint8_t* tokenizer_tok_bytes(const Tokenizer* t) { return t->d_tok_bytes; }
@@ -393,7 +483,8 @@ int tokenizer_encode(Tokenizer* t, const uint8_t* text_dev, int64_t n_bytes,
                      int64_t* row_tok_off_dev, cudaStream_t stream) {
   if (n_rows <= 0) return 0;
   if (t->reserve(n_bytes)) return -1;
-  TokTables tb{t->d_cls, t->d_hkeys, t->d_hvals, t->hmask, t->d_byte_to_id, t->digits};
+  TokTables tb{t->d_cls,    t->d_hkeys,  t->d_hvals,  t->hmask, t->d_byte_to_id, t->digits,
+               t->d_fkeys,  t->d_fslots, t->d_farena, t->fmask};
   const int64_t n1 = n_bytes + 1;
   SB_CUDA_CHECK(cudaMemsetAsync(t->d_flags, 0, n1, stream));
   SB_CUDA_CHECK(cudaMemsetAsync(t->d_cnt, 0, n1 * sizeof(int32_t), stream));

@@ -87,11 +87,23 @@ L.register("sb200_engine_stream", C.c_void_p, [C.c_void_p])
 L.register("sb200_tokenizer_create", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                                C.POINTER(C.c_void_p)])
+L.register("sb200_tokenizer_set_word_overrides", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p,
+                                                           C.c_void_p, C.c_int])
 L.register("sb200_tokenizer_destroy", None, [C.c_void_p])
 L.register("sb200_tokenizer_encode", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                                C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p])
 L.register("sb200_tokenizer_decode", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                                C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p])
+
+
+def word_override_arrays(v: VB.Vocab):
+    """Vocab.word_overrides -> (flat tokens, offsets[n+1], ids), int32, as the C-ABI takes them."""
+    seqs = v.word_overrides or []
+    off = np.zeros(len(seqs) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(s) for s, _ in seqs])
+    toks = np.asarray([t for s, _ in seqs for t in s], dtype=np.int32)
+    ids = np.asarray([e for _, e in seqs], dtype=np.int32)
+    return np.ascontiguousarray(toks), off, np.ascontiguousarray(ids)
 
 
 class ResultC(C.Structure):          # sb200_result (include/sutro_b200.h)
@@ -237,6 +249,10 @@ class GpuTokenizer:
                 cls.ctypes.data, v.digits,
                 blob.ctypes.data, off.ctypes.data, v.vocab_size, C.byref(h)))
         self._h = h
+        if v.word_overrides:      # the tokenizer file sets ignore_merges (vocab.Vocab)
+            toks, off, ids = word_override_arrays(v)
+            L.check(L.lib().sb200_tokenizer_set_word_overrides(
+                h, toks.ctypes.data, off.ctypes.data, ids.ctypes.data, len(ids)))
 
     def __del__(self):
         try:

@@ -91,13 +91,15 @@ def load_tokenizer_json(path: str, family: str, vocab_size: Optional[int] = None
             continue          # a merge whose parts or result are not tokens can never apply
         merges.append((int(r2e[real_vocab[a]]), int(r2e[real_vocab[b]])))
         merged_ids.append(int(r2e[real_vocab[ab]]))
+    word_overrides = None
     if model.get("ignore_merges"):
         # `ignore_merges` (Llama-3 files set it): a pre-token that is itself in the vocabulary
-        # is emitted as that token without running the merges.  The GPU BPE always merges, so
-        # the flag is honoured by proof: it is a no-op exactly when merging every vocabulary
-        # string reproduces its own token — checked here for all of them; otherwise refuse.
+        # is emitted as that token without running the merges.  That differs from plain BPE only
+        # for entries whose merges build something else: list those, with the sequence their
+        # merges do build — the GPU tokenizer replaces exactly those sequences (two byte strings
+        # never merge to the same tokens, so the replacement is exact).
         rank = {pair: (i, merged_ids[i]) for i, pair in reversed(list(enumerate(merges)))}
-        bad = 0
+        word_overrides = []
         for e, tb in enumerate(token_bytes):
             if len(tb) < 2:
                 continue
@@ -111,20 +113,20 @@ def load_tokenizer_json(path: str, family: str, vocab_size: Optional[int] = None
                 if best is None:
                     break
                 seq[bi:bi + 2] = [best[1]]
-            if seq != [e]:
-                bad += 1
-        if bad and os.environ.get("SB200_ALLOW_IGNORE_MERGES_MISMATCH") != "1":
-            raise ValueError(
-                f"{path}: model.ignore_merges is true and {bad} vocabulary entries are not what "
-                "their merges produce — a word equal to one of those entries would get other ids "
-                "here than under `tokenizers` (same text after decoding, different tokens than the "
-                "model was trained on).  Set SB200_ALLOW_IGNORE_MERGES_MISMATCH=1 to load anyway.")
+            if len(seq) >= 2:
+                if len(seq) > 32:
+                    raise ValueError(
+                        f"{path}: model.ignore_merges is true and vocabulary entry {e} merges to "
+                        f"{len(seq)} tokens; the GPU tokenizer's whole-word table holds sequences "
+                        "of at most 32")
+                word_overrides.append((tuple(seq), e))
     specials = {name: int(r2e[i]) for name, i in added.items()}
     need = "<|im_end|>" if family == "qwen3" else "<|eot_id|>"
     if need not in specials:
         raise ValueError(f"{path}: special token {need!r} (end of turn) is missing")
     return VB.Vocab(family, size, token_bytes, merges, specials, digits,
-                    merged_ids=merged_ids, id_map=e2r, normalize_nfc=norm is not None)
+                    merged_ids=merged_ids, id_map=e2r, normalize_nfc=norm is not None,
+                    word_overrides=word_overrides)
 
 
 def _pretokenizer_digits(pre: Optional[Dict[str, Any]], path: str) -> Optional[int]:

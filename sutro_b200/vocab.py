@@ -44,6 +44,11 @@ class Vocab:
     merged_ids: Optional[List[int]] = None
     id_map: Optional[np.ndarray] = None
     normalize_nfc: bool = False         # the tokenizer file asks for NFC-normalised input
+    # `ignore_merges` of the tokenizer file (Llama-3): a pre-token that is itself a vocabulary
+    # entry is emitted as that token without merging.  None = flag off.  When on: the entries
+    # whose merges do not rebuild them, as (the sequence their merges do build, entry id) —
+    # what the GPU tokenizer needs to honour the flag (sb200_tokenizer_set_word_overrides).
+    word_overrides: Optional[List[Tuple[Tuple[int, ...], int]]] = None
 
     def to_real_ids(self, ids):
         """engine token ids -> the tokenizer file's ids (identity for synthetic vocabularies)"""

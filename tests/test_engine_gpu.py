@@ -125,6 +125,31 @@ def test_gpu_tokenizer_matches_oracle(name):
         assert b[boff[i]:boff[i + 1]].tobytes() == t.encode("utf-8")
 
 
+def test_gpu_tokenizer_honours_ignore_merges(tmp_path):
+    """A tokenizer file with model.ignore_merges (Llama-3): pre-tokens that are vocabulary
+    entries come out as that entry — the GPU tokenizer (whole-word override table) against the
+    oracle and against `tokenizers` reading the same file."""
+    from test_pretrained_cpu import ROWS_TXT, ignore_merges_vocab, override_texts
+    from sutro_b200.engine import GpuTokenizer
+    _, hf, loaded = ignore_merges_vocab(tmp_path)
+    tok = GpuTokenizer(loaded, torch.device("cuda:0"))
+    ref = RefTokenizer(loaded)
+    texts = override_texts(loaded) + ROWS_TXT + ROWS
+    hits = 0
+    for t, g in zip(texts, tok.encode(texts)):
+        assert g == ref.encode(t), repr(t)
+        assert loaded.to_real_ids(g) == hf.encode(t, add_special_tokens=False).ids, repr(t)
+        hits += len(g) == 1 and any(g[0] == e for _, e in loaded.word_overrides)
+    assert hits >= 3
+    # the same vocabulary without the flag: the table is empty and plain BPE comes back
+    import dataclasses
+    plain_v = dataclasses.replace(loaded, word_overrides=None)
+    plain = GpuTokenizer(plain_v, torch.device("cuda:0"))
+    ref_plain = RefTokenizer(plain_v)
+    for t, g in zip(texts, plain.encode(texts)):
+        assert g == ref_plain.encode(t), repr(t)
+
+
 @pytest.mark.parametrize("name", ["tiny-qwen3", "tiny-qwen3-g4", "tiny-llama"])
 def test_unconstrained_greedy_matches_oracle(name):
     spec, w, v, eng = build(name, max_slots=8, max_prefill_tokens=512)

@@ -16,6 +16,10 @@ TEXTS = ["Hello, world!", "  leading spaces and 12345 numbers", "naÃ¯ve cafÃ© â€
          "æ—¥æœ¬èªžã®ãƒ†ã‚­ã‚¹ãƒˆ ðŸ™‚", "tabs\tand\nnewlines\r\n", "it's the model's 1st re-run", ""]
 
 
+ROWS_TXT = ["Great camera and build quality, would buy again!", "don't DON'T we'LL 1234567 3.14",
+            "unicode: cafÃ© naÃ¯ve StraÃŸe æ±äº¬ Â½ ðŸ™‚ end", "   ", "\n\n a"]
+
+
 def gpt2_ordered_tokenizer(v: VB.Vocab):
     """A `tokenizers.Tokenizer` over the same merges whose ids follow the GPT-2 convention:
     byte tokens 0..255 in bytes_to_unicode order, merge results in rank order after them."""
@@ -168,37 +172,58 @@ def test_real_pretokenizer_patterns_and_normalizers(tmp_path):
     assert _nfc_rows(["eÌ", None, "plain", 3]) == ["Ã©", None, "plain", 3]
 
 
-def test_ignore_merges_is_honoured_by_proof_or_refused(tmp_path, monkeypatch):
-    """Llama-3 tokenizer files set model.ignore_merges (a pre-token that is itself a vocabulary
-    entry is emitted whole).  The GPU BPE always merges, so the loader PROVES the flag is a no-op
-    â€” merging every vocabulary string must reproduce its own token â€” and otherwise refuses to
-    load (or loads with an explicit opt-in), never serving other ids silently."""
-    v = VB.build_vocab("llama", 2048, seed=0, n_trained=600)
-    hf = gpt2_ordered_tokenizer(v)
+def ignore_merges_vocab(tmp_path, family="llama"):
+    """A tokenizer.json with model.ignore_merges = true over the synthetic vocabulary (which has
+    entries that their own merges do not rebuild), the `tokenizers` object for it and the loaded
+    Vocab.  Shared with the GPU test."""
+    from tokenizers import Tokenizer
+    v = VB.build_vocab(family, 2048, seed=0, n_trained=600)
     path = str(tmp_path / "tokenizer.json")
-    hf.save(path)
+    gpt2_ordered_tokenizer(v).save(path)
     tj = json.load(open(path))
-    assert PT.load_tokenizer_json(path, "llama").vocab_size > 0      # flag absent: loads
     tj["model"]["ignore_merges"] = True
     json.dump(tj, open(path, "w"))
-    # does merging reproduce every entry of this vocabulary?  (count with the oracle's BPE)
-    monkeypatch.setenv("SB200_ALLOW_IGNORE_MERGES_MISMATCH", "1")
-    loaded = PT.load_tokenizer_json(path, "llama")
+    return path, Tokenizer.from_file(path), PT.load_tokenizer_json(path, family)
+
+
+def override_texts(loaded):
+    """Texts that exercise the whole-word rule: every overridden entry alone, glued to a
+    letter, and inside a sentence."""
+    texts = []
+    for _, e in loaded.word_overrides:
+        try:
+            w = loaded.token_bytes[e].decode("utf-8")
+        except UnicodeDecodeError:
+            continue
+        texts += [w, "x" + w, "so " + w.strip() + " and" + w + w + "."]
+    return texts
+
+
+def test_ignore_merges_whole_words_match_tokenizers(tmp_path):
+    """Llama-3 tokenizer files set model.ignore_merges: a pre-token that is itself a vocabulary
+    entry is emitted as that token without merging.  The loader lists the entries for which that
+    differs from plain BPE (Vocab.word_overrides); the oracle restates the rule; both are pinned
+    against `tokenizers` reading the same file."""
+    import dataclasses
+    path, hf, loaded = ignore_merges_vocab(tmp_path)
+    assert loaded.word_overrides, "the synthetic vocabulary has entries its merges do not rebuild"
     ref = RefTokenizer(loaded)
-    mismatches = sum(1 for e, tb in enumerate(loaded.token_bytes)
-                     if len(tb) >= 2 and ref._bpe(tb) != [e])
-    monkeypatch.delenv("SB200_ALLOW_IGNORE_MERGES_MISMATCH")
-    if mismatches:
-        with pytest.raises(ValueError, match=f"ignore_merges is true and {mismatches} vocabulary"):
-            PT.load_tokenizer_json(path, "llama")
-    else:
-        assert PT.load_tokenizer_json(path, "llama").vocab_size == loaded.vocab_size
-    # a vocabulary reduced to its byte tokens and first merges is consistent: accepted
-    keep = dict(list(tj["model"]["vocab"].items())[:256 + 40])
-    tj["model"]["vocab"] = keep
-    tj["model"]["merges"] = [m for m in tj["model"]["merges"]
-                             if "".join(m if isinstance(m, list) else m.split(" ")) in keep][:40]
-    tj["added_tokens"] = [dict(a, id=len(keep) + i) for i, a in enumerate(tj["added_tokens"])]
+    plain = RefTokenizer(dataclasses.replace(loaded, word_overrides=None))
+    hits = 0
+    for text in override_texts(loaded) + ROWS_TXT:
+        want = hf.encode(text, add_special_tokens=False).ids
+        assert loaded.to_real_ids(ref.encode(text)) == want, repr(text)
+    for seq, e in loaded.word_overrides:
+        try:
+            w = loaded.token_bytes[e].decode("utf-8")
+        except UnicodeDecodeError:
+            continue
+        if ref.pretokenize(w) == [w]:
+            hits += 1
+            assert ref.encode(w) == [e] and plain.encode(w) == list(seq) and len(seq) >= 2
+    assert hits >= 3
+    # flag absent: nothing to override, plain BPE everywhere
+    tj = json.load(open(path))
+    del tj["model"]["ignore_merges"]
     json.dump(tj, open(path, "w"))
-    small = PT.load_tokenizer_json(path, "llama")
-    assert len(small.merges) > 0
+    assert PT.load_tokenizer_json(path, "llama").word_overrides is None
