@@ -177,13 +177,14 @@ _FRAME_ROWS = ["", "a", None, "héllo wörld", "x" * 40] + [f"row {i} " + "y" * 
                                                            for i in range(31)]
 
 
-def _worker_frame(rank, world, port, balance, embedding, q):
+def _worker_frame(rank, world, port, balance, embedding, q, frame_rows=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from sutro_b200.sharding import infer_frame_sharded
         eng = _CpuEngine(rank, embedding)
-        out = infer_frame_sharded(eng, _FRAME_ROWS if rank == 0 else None, src=0, balance=balance,
+        frame_rows = _FRAME_ROWS if frame_rows is None else frame_rows
+        out = infer_frame_sharded(eng, frame_rows if rank == 0 else None, src=0, balance=balance,
                                   suffix="!")
         if rank == 0:
             q.put((out.get("outputs"), None if out.get("embeddings") is None
@@ -191,7 +192,8 @@ def _worker_frame(rank, world, port, balance, embedding, q):
                    out["stats"]["n_gpus"]))
         else:
             assert out is None
-        assert eng.seen_row_ids is not None       # rows keep their job-wide ids on every rank
+        if len(frame_rows) >= world:              # rows keep their job-wide ids on every rank
+            assert eng.seen_row_ids is not None
     finally:
         dist.destroy_process_group()
 
@@ -227,6 +229,30 @@ def test_infer_frame_sharded_world2_is_positional(balance, embedding):
     else:
         assert outputs == [f"{rows[i].upper()}@{owner[i]}!" for i in range(len(rows))]
     assert {owner[i] for i in range(len(rows))} == {0, 1}
+
+
+@pytest.mark.parametrize("world,frame_rows", [(3, None), (3, ["only one", "and another"])])
+def test_infer_frame_sharded_odd_world_and_more_ranks_than_rows(world, frame_rows):
+    """Three ranks (uneven shards), and a frame with fewer rows than ranks (a rank with an empty
+    shard takes part in the broadcast and the gather and contributes nothing)."""
+    from sutro_b200.sharding import snake_assignment
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_frame, args=(r, world, port, "bytes", False, q, frame_rows))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    outputs, _, rows_done, n_gpus = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    rows = ["" if r is None else r for r in (_FRAME_ROWS if frame_rows is None else frame_rows)]
+    shards = snake_assignment([len(r.encode()) for r in rows], world)
+    owner = {int(i): r for r, s in enumerate(shards) for i in s}
+    assert rows_done == len(rows) and n_gpus == world
+    assert outputs == [f"{rows[i].upper()}@{owner[i]}!" for i in range(len(rows))]
+    assert len(set(owner.values())) == min(world, len(rows))
 
 
 def test_infer_frame_sharded_single_process_matches():
