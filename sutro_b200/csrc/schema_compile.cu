@@ -6,14 +6,15 @@
 // C-ABI, so that a host in any language can pass the JSON text and get the automaton the
 // engine's mask/sampler kernels consume (sb200_job.fsm_*).  It restates the core of the Python
 // compiler (sutro_b200/schema_fsm.py: JSON Schema -> NFA of byte sets -> subset construction
-// -> trim) for the constructs Pydantic emits for plain models:
-//   objects (declared properties, in declaration order), strings (min/maxLength), integers and
-//   numbers (inclusive / exclusive bounds as exact digit automata), booleans, null, arrays
-//   (items, min/maxItems), enum / const, anyOf / oneOf, allOf of compatible parts, $ref into
+// -> trim) for the constructs Pydantic emits:
+//   objects (declared properties, in declaration order; Dict[str, T] as additionalProperties
+//   with propertyNames / min/maxProperties), strings (min/maxLength; formats date, time,
+//   date-time, uuid), integers and numbers (inclusive / exclusive bounds as exact digit
+//   automata), booleans, null, arrays (items, min/maxItems; tuples via prefixItems; uniqueItems
+//   over small enumerations), enum / const, anyOf / oneOf, allOf of compatible parts, $ref into
 //   $defs (recursion unrolled to a fixed depth), type lists.
-// Keywords that would constrain the output and are not handled here (pattern, format,
-// multipleOf, prefixItems, uniqueItems, additionalProperties maps, ...) are an ERROR, never
-// ignored — the Python host compiles those.  tests/test_schema_native_cpu.py checks that the
+// Keywords that would constrain the output and are not handled here (pattern, the other
+// formats, multipleOf, ...) are an ERROR, never ignored — the Python host compiles those.  tests/test_schema_native_cpu.py checks that the
 // automata accept exactly the same language as the Python compiler's, schema by schema.
 //
 // Host-only code (no kernels); compiled by nvcc with the rest of the library.
@@ -701,10 +702,48 @@ struct Compiler {
       static const std::set<std::string> plain = {"password", "binary", "byte", "regex", "path",
                                                   "file-path", "directory-path"};
       const JVal* f = sch.get("format");
-      if (f->t != JVal::Str || !plain.count(f->s))
-        fail("string formats are not supported by the native schema compiler (use the Python host)");
+      if (f->t != JVal::Str) fail("format must be a string");
+      if (!plain.count(f->s)) {
+        // the formats Pydantic emits for date / time / datetime / UUID fields, as the same
+        // sound subsets the Python compiler uses (schema_fsm.py _FORMATS: days stop at 28)
+        if (sch.has("minLength") || has_hi)
+          fail("format together with minLength / maxLength is not supported by the native schema "
+               "compiler (use the Python host)");
+        Frag body;
+        if (f->s == "date") {
+          body = fmt_date();
+        } else if (f->s == "time") {
+          body = fmt_time();
+        } else if (f->s == "date-time") {
+          body = b.seq({fmt_date(), b.lit("T"), fmt_time(), b.lit("Z")});
+        } else if (f->s == "uuid") {
+          body = fmt_uuid();
+        } else {
+          fail("string format '" + f->s + "' is not supported by the native schema compiler (use "
+               "the Python host)");
+        }
+        return b.seq({b.lit("\""), body, b.lit("\"")});
+      }
     }
     return b.json_string(lo, hi);
+  }
+  Frag digit(char lo_c = '0', char hi_c = '9') { return b.bset(Mask::rng(lo_c, hi_c)); }
+  Frag fmt_date() {   // [12]\d{3}-(0[1-9]|1[0-2])-(0[1-9]|1\d|2[0-8])
+    const Frag month = b.alt({b.seq({b.lit("0"), digit('1', '9')}), b.seq({b.lit("1"), digit('0', '2')})});
+    const Frag day = b.alt({b.seq({b.lit("0"), digit('1', '9')}), b.seq({b.lit("1"), digit()}),
+                            b.seq({b.lit("2"), digit('0', '8')})});
+    return b.seq({digit('1', '2'), digit(), digit(), digit(), b.lit("-"), month, b.lit("-"), day});
+  }
+  Frag fmt_time() {   // ([01]\d|2[0-3]):[0-5]\d:[0-5]\d
+    const Frag hour = b.alt({b.seq({digit('0', '1'), digit()}), b.seq({b.lit("2"), digit('0', '3')})});
+    return b.seq({hour, b.lit(":"), digit('0', '5'), digit(), b.lit(":"), digit('0', '5'), digit()});
+  }
+  Frag fmt_uuid() {   // 8-4-[1-5]3-[89ab]3-12 lower-case hex
+    const Mask hex = Mask::rng('0', '9') | Mask::rng('a', 'f');
+    auto hexes = [&](int k) { return b.rep([&] { return b.bset(hex); }, k, k); };
+    Mask variant = Mask::of('8') | Mask::of('9') | Mask::of('a') | Mask::of('b');
+    return b.seq({hexes(8), b.lit("-"), hexes(4), b.lit("-"), digit('1', '5'), hexes(3), b.lit("-"),
+                  b.bset(variant), hexes(3), b.lit("-"), hexes(12)});
   }
 
   // ---- arrays ----
@@ -716,15 +755,15 @@ struct Compiler {
     }();
     const JVal* items = sch.get("items");
     if (!items) items = &kEmptyObj;
-    if (sch.has("prefixItems") && !sch.get("prefixItems")->is_null())
-      fail("prefixItems is not supported by the native schema compiler (use the Python host)");
     const int lo = sch.has("minItems") ? static_cast<int>(as_int(*sch.get("minItems"), "minItems")) : 0;
     const bool has_hi = sch.has("maxItems") && !sch.get("maxItems")->is_null();
+    if (sch.has("prefixItems") && !sch.get("prefixItems")->is_null())
+      return tuple(sch, *sch.get("prefixItems"), *items, lo,
+                   has_hi ? static_cast<int>(as_int(*sch.get("maxItems"), "maxItems")) : -1);
     const int hi = has_hi ? static_cast<int>(as_int(*sch.get("maxItems"), "maxItems"))
                           : std::max(lo, lim.max_array_items);
     if (hi < lo) fail("array length range is empty");
-    if (truthy(sch.get("uniqueItems")))
-      fail("uniqueItems is not supported by the native schema compiler (use the Python host)");
+    if (truthy(sch.get("uniqueItems"))) return unique(*items, lo, hi);
     if (hi == 0) return b.lit("[]");
     if (items->t == JVal::Bool && !items->b) {
       if (lo > 0) fail("array admits no items but minItems > 0");
@@ -748,6 +787,141 @@ struct Compiler {
     return b.seq({b.lit("["), inner, b.lit("]")});
   }
 
+  // prefixItems: positional schemas, then `items` for the rest (false = nothing more);
+  // hi < 0 = no maxItems (schema_fsm.py _tuple)
+  Frag tuple(const JVal& sch, const JVal& prefix, const JVal& items, int lo, int hi) {
+    if (prefix.t != JVal::Arr) fail("prefixItems must be an array");
+    if (truthy(sch.get("uniqueItems"))) fail("uniqueItems with prefixItems is not supported");
+    const bool items_false = items.t == JVal::Bool && !items.b;
+    const int np = static_cast<int>(prefix.a.size());
+    const int n = hi < 0 ? np : std::min(np, hi);
+    if (lo > n && items_false) fail("minItems exceeds the number of prefixItems");
+    const int extra_lo = std::max(lo - n, 0);
+    const int extra_hi = items_false ? 0 : (hi >= 0 ? hi - n : std::max(extra_lo, 0));
+    std::vector<Frag> alts;
+    for (int take = std::max(std::min(lo, n), 0); take <= n; ++take) {
+      if (take < n && extra_lo > 0) continue;
+      std::vector<Frag> parts;
+      for (int i = 0; i < take; ++i) {
+        if (i) parts.push_back(b.lit(","));
+        parts.push_back(node(prefix.a[i]));
+      }
+      if (take == n && extra_hi > 0) {
+        Frag more;
+        if (n > 0) {
+          more = b.rep([&] { return b.seq({b.lit(","), node(items)}); }, extra_lo, extra_hi);
+        } else {
+          const Frag first = node(items);
+          const Frag rest = b.rep([&] { return b.seq({b.lit(","), node(items)}); },
+                                  std::max(extra_lo - 1, 0), extra_hi - 1);
+          more = b.seq({first, rest});
+          if (extra_lo == 0) more = b.opt(more);
+        }
+        parts.push_back(more);
+      }
+      if (parts.empty()) {
+        alts.push_back(b.lit("[]"));
+      } else {
+        std::vector<Frag> all{b.lit("[")};
+        all.insert(all.end(), parts.begin(), parts.end());
+        all.push_back(b.lit("]"));
+        alts.push_back(b.seq(all));
+      }
+    }
+    return b.alt_or_single(alts);
+  }
+
+  // uniqueItems needs memory a DFA does not have; small enumerations are spelled out
+  // (schema_fsm.py _unique)
+  Frag unique(const JVal& items_in, int lo, int hi) {
+    const JVal* nd = &items_in;
+    if (nd->t == JVal::Obj && nd->has("$ref")) {
+      if (nd->get("$ref")->t != JVal::Str) fail("$ref must be a string");
+      nd = &resolve(nd->get("$ref")->s);
+    }
+    std::vector<std::string> values;   // compact JSON text of each admissible item
+    bool known = false;
+    if (nd->t == JVal::Obj) {
+      if (nd->has("enum") && nd->get("enum")->t == JVal::Arr) {
+        for (auto& v : nd->get("enum")->a) values.push_back(dump_compact(v));
+        known = true;
+      } else if (nd->has("const")) {
+        values.push_back(dump_compact(*nd->get("const")));
+        known = true;
+      } else if (nd->has("type") && nd->get("type")->t == JVal::Str && nd->get("type")->s == "boolean") {
+        values = {"true", "false"};
+        known = true;
+      }
+    }
+    if (!known || values.size() > 6)
+      fail("uniqueItems is only supported for arrays over at most 6 enumerated values");
+    std::vector<std::string> distinct;
+    for (auto& v : values)
+      if (std::find(distinct.begin(), distinct.end(), v) == distinct.end()) distinct.push_back(v);
+    std::vector<std::string> arrays;
+    const int top = std::min<int>(hi, static_cast<int>(distinct.size()));
+    std::vector<int> pick;
+    std::vector<bool> used(distinct.size(), false);
+    std::function<void(int)> rec = [&](int k) {
+      if (static_cast<int>(pick.size()) == k) {
+        std::string a = "[";
+        for (size_t i = 0; i < pick.size(); ++i) a += (i ? "," : "") + distinct[pick[i]];
+        arrays.push_back(a + "]");
+        return;
+      }
+      for (size_t i = 0; i < distinct.size(); ++i) {
+        if (used[i]) continue;
+        used[i] = true;
+        pick.push_back(static_cast<int>(i));
+        rec(k);
+        pick.pop_back();
+        used[i] = false;
+      }
+    };
+    for (int k = lo; k <= top; ++k) rec(k);
+    if (arrays.empty()) fail("uniqueItems: no array satisfies the length bounds");
+    return b.literals(arrays);
+  }
+
+  // Dict[str, T]: free keys (propertyNames applies), values of one schema; duplicate keys are
+  // not excluded (schema_fsm.py _mapping)
+  Frag mapping(const JVal& sch, const JVal& value_schema) {
+    const int lo = sch.has("minProperties") ? static_cast<int>(as_int(*sch.get("minProperties"), "minProperties")) : 0;
+    const bool has_hi = sch.has("maxProperties") && !sch.get("maxProperties")->is_null();
+    const int hi = has_hi ? static_cast<int>(as_int(*sch.get("maxProperties"), "maxProperties"))
+                          : std::max(lo, lim.max_array_items);
+    if (hi < lo) fail("property count range is empty");
+    JVal names;
+    names.t = JVal::Obj;
+    if (const JVal* pn = sch.get("propertyNames"))
+      if (pn->t == JVal::Obj) names = *pn;
+    auto set_key = [&](const char* k, JVal v) {
+      for (auto& kv : names.o)
+        if (kv.first == k) return;
+      names.o.emplace_back(k, std::move(v));
+    };
+    JVal str_t;
+    str_t.t = JVal::Str;
+    str_t.s = "string";
+    set_key("type", str_t);
+    if (names.get("type")->t != JVal::Str || names.get("type")->s != "string")
+      fail("propertyNames must describe strings");
+    if (!names.has("minLength") && !names.has("pattern") && !names.has("enum") &&
+        !names.has("format") && !names.has("const")) {
+      JVal one;      // keep keys non-empty unless the schema says otherwise
+      one.t = JVal::Num;
+      one.s = "1";
+      set_key("minLength", one);
+    }
+    if (hi == 0) return b.lit("{}");
+    auto entry = [&] { return b.seq({node(names), b.lit(":"), node(value_schema)}); };
+    const Frag first = entry();
+    const Frag rest = b.rep([&] { return b.seq({b.lit(","), entry()}); }, std::max(lo - 1, 0), hi - 1);
+    Frag inner = b.seq({first, rest});
+    if (lo == 0) inner = b.opt(inner);
+    return b.seq({b.lit("{"), inner, b.lit("}")});
+  }
+
   // ---- objects ----
   Frag obj(const JVal& sch) {
     const JVal* props = sch.get("properties");
@@ -757,9 +931,14 @@ struct Compiler {
     if (no_props) {
       const bool addl_dict = addl && addl->t == JVal::Obj;
       const bool addl_true = addl && addl->t == JVal::Bool && addl->b;
-      if (addl_dict || (addl_true && (min_p != 0 || truthy(sch.get("propertyNames")))))
-        fail("free-key objects (additionalProperties / propertyNames) are not supported by the "
-             "native schema compiler (use the Python host)");
+      if (addl_dict || (addl_true && (min_p != 0 || truthy(sch.get("propertyNames"))))) {
+        static const JVal kAny = [] {
+          JVal v;
+          v.t = JVal::Obj;
+          return v;
+        }();
+        return mapping(sch, addl_dict ? *addl : kAny);
+      }
       if (min_p > 0) fail("minProperties > 0 on an object without properties");
       return b.lit("{}");
     }

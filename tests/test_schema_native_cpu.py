@@ -70,6 +70,15 @@ class Node(BaseModel):
     children: List["Node"] = Field(default_factory=list, max_length=2)
 
 
+class Event(BaseModel):
+    when: __import__("datetime").datetime
+    day: __import__("datetime").date
+    ident: __import__("uuid").UUID
+    pair: __import__("typing").Tuple[int, bool]
+    tags: __import__("typing").Set[Literal["a", "b"]]
+    counts: __import__("typing").Dict[str, bool]
+
+
 SMALL = FsmLimits(max_string_chars=6, max_array_items=2, max_int_digits=4, max_frac_digits=2)
 CASES = [
     (Sentiment.model_json_schema(), None),
@@ -98,6 +107,26 @@ CASES = [
     ({"type": "object"}, None),
     ({}, SMALL),
     ({"type": "object", "properties": {"kéy \"q\"": {"type": "null"}}}, None),
+    # what Pydantic emits for datetime / date / time / UUID, Tuple, Set and Dict fields
+    (Event.model_json_schema(), SMALL),
+    ({"type": "string", "format": "date"}, None),
+    ({"type": "string", "format": "time"}, None),
+    ({"type": "string", "format": "date-time"}, None),
+    ({"type": "string", "format": "uuid"}, None),
+    ({"type": "array", "prefixItems": [{"type": "integer", "minimum": 0, "maximum": 9}, {"type": "boolean"}],
+      "items": False}, None),
+    ({"type": "array", "prefixItems": [{"type": "boolean"}, {"type": "null"}], "minItems": 1,
+      "items": {"type": "integer", "minimum": 0, "maximum": 3}, "maxItems": 4}, None),
+    ({"type": "array", "prefixItems": [{"enum": ["a", "b"]}], "minItems": 0}, None),
+    ({"type": "array", "prefixItems": [], "items": {"type": "boolean"}, "maxItems": 2}, None),
+    ({"type": "array", "items": {"enum": [1, "two", None]}, "uniqueItems": True}, None),
+    ({"type": "array", "items": {"type": "boolean"}, "uniqueItems": True, "minItems": 1}, None),
+    ({"type": "array", "items": {"const": {"k": [1]}}, "uniqueItems": True}, None),
+    ({"type": "object", "additionalProperties": {"type": "integer", "minimum": 0, "maximum": 5}}, SMALL),
+    ({"type": "object", "additionalProperties": {"type": "boolean"}, "minProperties": 1, "maxProperties": 2,
+      "propertyNames": {"enum": ["x", "y"]}}, None),
+    ({"type": "object", "additionalProperties": True, "minProperties": 1,
+      "propertyNames": {"maxLength": 2}}, SMALL),
 ]
 
 
@@ -114,11 +143,12 @@ def test_native_schema_compiler_accepts_the_same_language(schema, limits):
 
 
 @pytest.mark.parametrize("schema", [
-    {"type": "string", "pattern": "^[a-z]+$"}, {"type": "string", "format": "date"},
+    {"type": "string", "pattern": "^[a-z]+$"}, {"type": "string", "format": "email"},
+    {"type": "string", "format": "date", "maxLength": 10},
     {"type": "integer", "minimum": 0, "maximum": 10, "multipleOf": 2},
-    {"type": "array", "prefixItems": [{"type": "integer"}]},
-    {"type": "array", "items": {"enum": [1, 2]}, "uniqueItems": True},
-    {"type": "object", "additionalProperties": {"type": "integer"}},
+    {"type": "array", "items": {"type": "integer"}, "uniqueItems": True},
+    {"type": "array", "prefixItems": [{"type": "integer"}], "uniqueItems": True},
+    {"type": "object", "additionalProperties": {"type": "integer"}, "propertyNames": {"pattern": "^k"}},
     {"type": "string", "bogusKeyword": 1}, {"not": {"type": "string"}}, {"$ref": "http://x/y"},
     {"type": "integer", "minimum": 5, "maximum": 1},
 ])
