@@ -10,11 +10,11 @@
 //   objects (declared properties, in declaration order; Dict[str, T] as additionalProperties
 //   with propertyNames / min/maxProperties), strings (min/maxLength; formats date, time,
 //   date-time, uuid), integers and numbers (inclusive / exclusive bounds as exact digit
-//   automata), booleans, null, arrays (items, min/maxItems; tuples via prefixItems; uniqueItems
+//   automata; multipleOf over bounded ranges), booleans, null, arrays (items, min/maxItems; tuples via prefixItems; uniqueItems
 //   over small enumerations), enum / const, anyOf / oneOf, allOf of compatible parts, $ref into
 //   $defs (recursion unrolled to a fixed depth), type lists.
 // Keywords that would constrain the output and are not handled here (pattern, the other
-// formats, multipleOf, ...) are an ERROR, never ignored — the Python host compiles those.  tests/test_schema_native_cpu.py checks that the
+// formats, ...) are an ERROR, never ignored — the Python host compiles those.  tests/test_schema_native_cpu.py checks that the
 // automata accept exactly the same language as the Python compiler's, schema by schema.
 //
 // Host-only code (no kernels); compiled by nvcc with the rest of the library.
@@ -626,10 +626,54 @@ struct Compiler {
     const Frag more = b.rep([&] { return b.bset(digits); }, 0, lim.max_int_digits - 1);
     return b.alt({zero, b.seq({lead, more})});
   }
+  // multipleOf over a bounded range: the multiples are spelled out (schema_fsm.py _multiples)
+  Frag multiples(const JVal& sch, const Bounds& bd, bool integral) {
+    const JVal* m = sch.get("multipleOf");
+    if (m->t != JVal::Num) fail("multipleOf must be a number");
+    const Dec step = parse_dec(m->s);
+    if (step.neg || step.is_zero()) fail("multipleOf must be positive");
+    if (!bd.has_lo || !bd.has_hi) fail("multipleOf needs both a minimum and a maximum here");
+    const int f = std::max(0, std::max(-step.exp10, std::max(-bd.lo.exp10, -bd.hi.exp10)));
+    if (f > 12) fail("multipleOf: too many fraction digits");
+    bool e1, e2, e3;
+    const long long L = scaled_int(bd.lo, f, true, &e1), H = scaled_int(bd.hi, f, false, &e2),
+                    S = scaled_int(step, f, false, &e3);
+    if (L <= -kBig || H >= kBig || S >= kBig || S <= 0) fail("multipleOf: bounds out of range");
+    auto floor_div = [](long long a, long long b) {
+      long long q = a / b;
+      if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+      return q;
+    };
+    long long k0 = -floor_div(-L, S), k1 = floor_div(H, S);   // ceil(L/S), floor(H/S)
+    if (bd.lo_open && k0 * S == L) ++k0;
+    if (bd.hi_open && k1 * S == H) --k1;
+    if (k1 - k0 + 1 > lim.small_int_range)
+      fail("multipleOf over more than " + std::to_string(lim.small_int_range) +
+           " values is not supported");
+    long long p10 = 1;
+    for (int i = 0; i < f; ++i) p10 *= 10;
+    std::vector<std::string> words;
+    for (long long k = k0; k <= k1; ++k) {
+      const long long v = k * S;
+      if (integral && v % p10 != 0) continue;
+      const long long a = v < 0 ? -v : v;
+      std::string text = std::to_string(a / p10);
+      if (a % p10 != 0) {
+        std::string frac = std::to_string(a % p10);
+        frac.insert(0, static_cast<size_t>(f) - frac.size(), '0');
+        while (!frac.empty() && frac.back() == '0') frac.pop_back();
+        text += "." + frac;
+      }
+      if (v < 0) text.insert(0, "-");
+      words.push_back(text);
+    }
+    if (words.empty()) fail("numeric range is empty");
+    return b.literals(words);
+  }
+
   Frag integer(const JVal& sch) {
     const Bounds bd = bounds(sch);
-    if (sch.has("multipleOf") && !sch.get("multipleOf")->is_null())
-      fail("multipleOf is not supported by the native schema compiler (use the Python host)");
+    if (sch.has("multipleOf") && !sch.get("multipleOf")->is_null()) return multiples(sch, bd, true);
     bool has_lo = bd.has_lo, has_hi = bd.has_hi, exact;
     long long ilo = 0, ihi = 0;
     if (has_lo) {
@@ -658,8 +702,7 @@ struct Compiler {
   }
   Frag number(const JVal& sch) {
     const Bounds bd = bounds(sch);
-    if (sch.has("multipleOf") && !sch.get("multipleOf")->is_null())
-      fail("multipleOf is not supported by the native schema compiler (use the Python host)");
+    if (sch.has("multipleOf") && !sch.get("multipleOf")->is_null()) return multiples(sch, bd, false);
     if (!bd.has_hi && (!bd.has_lo || (bd.lo.is_zero() && !bd.lo_open))) {
       const Mask digits = Mask::rng(0x30, 0x39);
       Frag sign = kNone;

@@ -127,6 +127,12 @@ CASES = [
       "propertyNames": {"enum": ["x", "y"]}}, None),
     ({"type": "object", "additionalProperties": True, "minProperties": 1,
       "propertyNames": {"maxLength": 2}}, SMALL),
+    ({"type": "integer", "minimum": 0, "maximum": 10, "multipleOf": 2}, None),
+    ({"type": "integer", "minimum": -7, "exclusiveMaximum": 9, "multipleOf": 3}, None),
+    ({"type": "integer", "minimum": -3, "maximum": 3, "multipleOf": 1.5}, None),
+    ({"type": "number", "minimum": -1, "maximum": 1, "multipleOf": 0.25}, None),
+    ({"type": "number", "exclusiveMinimum": 0, "maximum": 0.3, "multipleOf": 0.05}, None),
+    ({"type": "number", "minimum": 10, "maximum": 100, "multipleOf": 12.5}, None),
 ]
 
 
@@ -145,7 +151,7 @@ def test_native_schema_compiler_accepts_the_same_language(schema, limits):
 @pytest.mark.parametrize("schema", [
     {"type": "string", "pattern": "^[a-z]+$"}, {"type": "string", "format": "email"},
     {"type": "string", "format": "date", "maxLength": 10},
-    {"type": "integer", "minimum": 0, "maximum": 10, "multipleOf": 2},
+    {"type": "integer", "minimum": 0, "multipleOf": 2}, {"type": "number", "minimum": 0, "maximum": 1, "multipleOf": 0},
     {"type": "array", "items": {"type": "integer"}, "uniqueItems": True},
     {"type": "array", "prefixItems": [{"type": "integer"}], "uniqueItems": True},
     {"type": "object", "additionalProperties": {"type": "integer"}, "propertyNames": {"pattern": "^k"}},
