@@ -294,11 +294,11 @@ void sb200_result_free(sb200_result* result);
  * DFA the engine consumes (sb200_job.fsm_trans / fsm_accept / fsm_final); caps for unbounded
  * strings / arrays / integers come from sb200_fsm_limits (NULL = defaults).  Supported:
  * objects with declared properties or free keys (additionalProperties maps), strings
- * (min/maxLength; formats date, time, date-time, uuid), integer / number bounds and multipleOf,
+ * (min/maxLength; formats date, time, date-time, uuid, email, uri, ipv4, duration), integer / number bounds and multipleOf,
  * booleans, null,
  * arrays (items, min/maxItems, prefixItems tuples, uniqueItems over small enumerations), enum,
  * const, anyOf / oneOf, compatible allOf, $ref into $defs, type lists.  A keyword outside that
- * set (pattern, other formats, ...) that would constrain the
+ * set (pattern, ...) that would constrain the
  * output is an error (-2 = argument error), never ignored.  The tables stay owned by the
  * schema handle until sb200_schema_destroy.
  * ---------------------------------------------------------------------- */

@@ -9,12 +9,12 @@
 // -> trim) for the constructs Pydantic emits:
 //   objects (declared properties, in declaration order; Dict[str, T] as additionalProperties
 //   with propertyNames / min/maxProperties), strings (min/maxLength; formats date, time,
-//   date-time, uuid), integers and numbers (inclusive / exclusive bounds as exact digit
+//   date-time, uuid, email, uri, ipv4, duration), integers and numbers (inclusive / exclusive bounds as exact digit
 //   automata; multipleOf over bounded ranges), booleans, null, arrays (items, min/maxItems; tuples via prefixItems; uniqueItems
 //   over small enumerations), enum / const, anyOf / oneOf, allOf of compatible parts, $ref into
 //   $defs (recursion unrolled to a fixed depth), type lists.
-// Keywords that would constrain the output and are not handled here (pattern, the other
-// formats, ...) are an ERROR, never ignored — the Python host compiles those.  tests/test_schema_native_cpu.py checks that the
+// Keywords that would constrain the output and are not handled here (pattern, ...) are an
+// ERROR, never ignored — the Python host compiles those.  tests/test_schema_native_cpu.py checks that the
 // automata accept exactly the same language as the Python compiler's, schema by schema.
 //
 // Host-only code (no kernels); compiled by nvcc with the rest of the library.
@@ -761,6 +761,17 @@ struct Compiler {
           body = b.seq({fmt_date(), b.lit("T"), fmt_time(), b.lit("Z")});
         } else if (f->s == "uuid") {
           body = fmt_uuid();
+        } else if (f->s == "email") {   // [a-z0-9]{1,12}@[a-z0-9]{1,12}\.(com|org|net)
+          body = b.seq({fmt_label(1), b.lit("@"), fmt_label(1), b.lit("."), fmt_tld()});
+        } else if (f->s == "uri") {     // https://[a-z0-9]{1,12}\.(com|org|net)(/[a-z0-9]{0,12})?
+          body = b.seq({b.lit("https://"), fmt_label(1), b.lit("."), fmt_tld(),
+                        b.opt(b.seq({b.lit("/"), fmt_label(0)}))});
+        } else if (f->s == "ipv4") {    // four octets 0..255 without leading zeros
+          body = b.seq({fmt_octet(), b.rep([&] { return b.seq({b.lit("."), fmt_octet()}); }, 3, 3)});
+        } else if (f->s == "duration") {   // PT(\d{1,2}H)?(\d{1,2}M)?\d{1,2}S
+          auto d12 = [&] { return b.rep([&] { return digit(); }, 1, 2); };
+          body = b.seq({b.lit("PT"), b.opt(b.seq({d12(), b.lit("H")})),
+                        b.opt(b.seq({d12(), b.lit("M")})), d12(), b.lit("S")});
         } else {
           fail("string format '" + f->s + "' is not supported by the native schema compiler (use "
                "the Python host)");
@@ -780,6 +791,15 @@ struct Compiler {
   Frag fmt_time() {   // ([01]\d|2[0-3]):[0-5]\d:[0-5]\d
     const Frag hour = b.alt({b.seq({digit('0', '1'), digit()}), b.seq({b.lit("2"), digit('0', '3')})});
     return b.seq({hour, b.lit(":"), digit('0', '5'), digit(), b.lit(":"), digit('0', '5'), digit()});
+  }
+  Frag fmt_label(int lo_n) {   // [a-z0-9]{lo_n,12}
+    const Mask m = Mask::rng('a', 'z') | Mask::rng('0', '9');
+    return b.rep([&] { return b.bset(m); }, lo_n, 12);
+  }
+  Frag fmt_tld() { return b.literals({"com", "org", "net"}); }
+  Frag fmt_octet() {   // 25[0-5]|2[0-4]\d|1\d\d|[1-9]?\d
+    return b.alt({b.seq({b.lit("25"), digit('0', '5')}), b.seq({b.lit("2"), digit('0', '4'), digit()}),
+                  b.seq({b.lit("1"), digit(), digit()}), b.seq({b.opt(digit('1', '9')), digit()})});
   }
   Frag fmt_uuid() {   // 8-4-[1-5]3-[89ab]3-12 lower-case hex
     const Mask hex = Mask::rng('0', '9') | Mask::rng('a', 'f');

@@ -113,6 +113,10 @@ CASES = [
     ({"type": "string", "format": "time"}, None),
     ({"type": "string", "format": "date-time"}, None),
     ({"type": "string", "format": "uuid"}, None),
+    ({"type": "string", "format": "email"}, None),
+    ({"type": "string", "format": "uri"}, None),
+    ({"type": "string", "format": "ipv4"}, None),
+    ({"type": "string", "format": "duration"}, None),
     ({"type": "array", "prefixItems": [{"type": "integer", "minimum": 0, "maximum": 9}, {"type": "boolean"}],
       "items": False}, None),
     ({"type": "array", "prefixItems": [{"type": "boolean"}, {"type": "null"}], "minItems": 1,
@@ -149,7 +153,7 @@ def test_native_schema_compiler_accepts_the_same_language(schema, limits):
 
 
 @pytest.mark.parametrize("schema", [
-    {"type": "string", "pattern": "^[a-z]+$"}, {"type": "string", "format": "email"},
+    {"type": "string", "pattern": "^[a-z]+$"}, {"type": "string", "format": "hostname"},
     {"type": "string", "format": "date", "maxLength": 10},
     {"type": "integer", "minimum": 0, "multipleOf": 2}, {"type": "number", "minimum": 0, "maximum": 1, "multipleOf": 0},
     {"type": "array", "items": {"type": "integer"}, "uniqueItems": True},
