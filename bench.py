@@ -711,6 +711,12 @@ def main():
                 eq = [a == b for a, b in zip(got, texts)]
                 cpu["outputs_equal"] = f"{sum(eq)}/{len(eq)}"
                 cpu["mismatch_min_margins"] = [m for m, e in zip(margins, eq) if not e]
+                # a row whose oracle run passed through a decision closer than the near-tie
+                # band of the parity tests (0.06 logit units, tests/test_engine_gpu.py) may
+                # legitimately come out differently: both arms round a 36-layer bf16 network
+                near = sum(1 for m, e in zip(margins, eq) if not e and m is not None and m < 0.06)
+                cpu["near_tie_band"] = 0.06
+                cpu["outputs_equal_or_inside_near_tie_band"] = f"{sum(eq) + near}/{len(eq)}"
                 cpu["engine_outputs_sample"] = got[:3]
                 log(f"cpu baseline done: {cpu['value']:.3f} rows/s, outputs equal {cpu['outputs_equal']}")
             except Exception as e:  # the baseline must not sink the benchmark line
